@@ -1,0 +1,97 @@
+// Shared device/host helpers for the a3t_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/a3t_b200.h"
+
+namespace a3t {
+
+// ---- error plumbing: never throw/exit across the C ABI ------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // returns A3T_OK or A3T_ERR_CUDA after cudaGetLastError
+
+#define A3T_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) {                                \
+      a3t::set_error(__VA_ARGS__);                \
+      return A3T_ERR_ARG;                         \
+    }                                             \
+  } while (0)
+
+// ---- dtype helpers ------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t i) {
+  return dtype == A3T_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, float v) {
+  if (dtype == A3T_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+// ---- stateless dropout mask (bit-identical twin: oracle/a3t_oracle.py::keep_mask) -----------
+__device__ __host__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+struct Drop {
+  uint32_t thr;      // keep iff (hash>>8) >= thr ; thr = (uint32)(p * 2^24)
+  float inv_keep;    // 1/(1-p)
+  uint32_t k0, k1;   // derived from seed and site
+  bool on;
+};
+__device__ __forceinline__ Drop make_drop(float p, const unsigned long long* seed_ptr, uint32_t site) {
+  Drop d;
+  d.on = p > 0.f;
+  d.thr = 0; d.inv_keep = 1.f; d.k0 = 0; d.k1 = 0;
+  if (d.on) {
+    unsigned long long seed = *seed_ptr;
+    d.thr = (uint32_t)(p * 16777216.0f);
+    d.inv_keep = 1.0f / (1.0f - p);
+    d.k0 = (uint32_t)(seed & 0xFFFFFFFFull) + site * 0x9E3779B9u;
+    d.k1 = (uint32_t)(seed >> 32);
+  }
+  return d;
+}
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  uint32_t x = (uint32_t)(idx & 0xFFFFFFFFull) ^ ((uint32_t)(idx >> 32) * 0x85EBCA6Bu);
+  x ^= d.k0;
+  x = fmix32(x);
+  x += d.k1;
+  x = fmix32(x);
+  return (x >> 8) >= d.thr;
+}
+__device__ __forceinline__ float drop_apply(const Drop& d, unsigned long long idx, float v) {
+  if (!d.on) return v;
+  return drop_keep(d, idx) ? v * d.inv_keep : 0.f;
+}
+
+// ---- warp / block reductions ---------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace a3t

@@ -1,0 +1,189 @@
+// Generic strided/batched GEMM on CUDA cores with fp32 accumulation.
+// This is the exact-fp32 parity path and the fallback for shapes the tcgen05 kernel (gemm_tc.cu)
+// does not take (K=80 pre-net, N=80 head, tiny position GEMM).  Same epilogue as the tensor-core
+// kernel.  See include/a3t_b200.h::a3t_gemm for the contract.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace a3t {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return A3T_ERR_CUDA;
+  }
+  return A3T_OK;
+}
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+// element fetchers --------------------------------------------------------------------------
+__device__ __forceinline__ float fetch_a(const A3tGemmDesc& d, const void* A, int m, int k) {
+  if (m >= d.M || k >= d.K) return 0.f;
+  if (d.mode == A3T_GEMM_CONV) {
+    int tap = k / d.cin, c = k - tap * d.cin;
+    int t = m % d.seq;
+    int ts = t + tap - d.pad;
+    if (ts < 0 || ts >= d.seq) return 0.f;
+    return load_as_f32(A, d.dtype_a, (int64_t)(m - t + ts) * d.sa_m + (int64_t)c * d.sa_k);
+  }
+  return load_as_f32(A, d.dtype_a, (int64_t)m * d.sa_m + (int64_t)k * d.sa_k);
+}
+__device__ __forceinline__ float fetch_b(const A3tGemmDesc& d, const void* B, int n, int k) {
+  if (n >= d.N || k >= d.K) return 0.f;
+  if (d.mode == A3T_GEMM_CONV) {
+    int tap = k / d.cin, c = k - tap * d.cin;
+    return load_as_f32(B, d.dtype_b, (int64_t)n * d.sb_n + (int64_t)tap * d.sb_tap + (int64_t)c * d.sb_k);
+  }
+  if (d.mode == A3T_GEMM_WGRAD) {
+    int tap = n / d.cin, c = n - tap * d.cin;
+    int t = k % d.seq;
+    int ts = t + tap - d.pad;
+    if (ts < 0 || ts >= d.seq) return 0.f;
+    return load_as_f32(B, d.dtype_b, (int64_t)(k - t + ts) * d.sb_k + (int64_t)c * d.sb_n);
+  }
+  return load_as_f32(B, d.dtype_b, (int64_t)n * d.sb_n + (int64_t)k * d.sb_k);
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const A3tGemmDesc d, const void* __restrict__ A0,
+                                                        const void* __restrict__ B0, void* __restrict__ C0,
+                                                        const float* __restrict__ bias,
+                                                        const float* __restrict__ res0,
+                                                        const void* __restrict__ mask0,
+                                                        const unsigned long long* __restrict__ seed) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int bz = blockIdx.z;
+  const int b1 = bz / d.batch2, b2 = bz - b1 * d.batch2;
+  const size_t esa = d.dtype_a == A3T_BF16 ? 2 : 4, esb = d.dtype_b == A3T_BF16 ? 2 : 4,
+               esc = d.dtype_c == A3T_BF16 ? 2 : 4, esm = d.dtype_mask == A3T_BF16 ? 2 : 4;
+  const void* A = (const char*)A0 + (b1 * d.sa_b1 + b2 * d.sa_b2) * (int64_t)esa;
+  const void* B = (const char*)B0 + (b1 * d.sb_b1 + b2 * d.sb_b2) * (int64_t)esb;
+  void* C = (char*)C0 + (b1 * d.sc_b1 + b2 * d.sc_b2) * (int64_t)esc;
+  const void* mask = mask0 ? (const char*)mask0 + (b1 * d.sc_b1 + b2 * d.sc_b2) * (int64_t)esm : nullptr;
+  const float* res = res0 ? res0 + (b1 * d.sr_b1 + b2 * d.sr_b2) : nullptr;
+
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  // loader mapping: if the reduction index is the contiguous one, let consecutive threads walk k.
+  const bool a_kfast = (d.mode == A3T_GEMM_WGRAD) ? false : (d.sa_k == 1);
+  const bool b_kfast = (d.mode == A3T_GEMM_WGRAD) ? false : (d.sb_k == 1);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < d.K; k0 += BK) {
+#pragma unroll
+    for (int e = 0; e < (BM * BK) / 256; e++) {
+      int idx = tid + e * 256;
+      int mm, kk;
+      if (a_kfast) { kk = idx & (BK - 1); mm = idx >> 4; } else { mm = idx & (BM - 1); kk = idx >> 6; }
+      As[kk][mm] = fetch_a(d, A, m0 + mm, k0 + kk);
+    }
+#pragma unroll
+    for (int e = 0; e < (BN * BK) / 256; e++) {
+      int idx = tid + e * 256;
+      int nn, kk;
+      if (b_kfast) { kk = idx & (BK - 1); nn = idx >> 4; } else { nn = idx & (BN - 1); kk = idx >> 6; }
+      Bs[kk][nn] = fetch_b(d, B, n0 + nn, k0 + kk);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; j++) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  Drop dr = make_drop(d.drop_p, seed, d.drop_site);
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    int m = m0 + ty * TM + i;
+    if (m >= d.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      int n = n0 + tx * TN + j;
+      if (n >= d.N) continue;
+      float v = d.alpha * acc[i][j];
+      if (bias) v += bias[n];
+      if (d.relu) v = fmaxf(v, 0.f);
+      int64_t coff;
+      if (d.mode == A3T_GEMM_WGRAD) {
+        int tap = n / d.cin, c = n - tap * d.cin;
+        coff = (int64_t)m * d.sc_m + (int64_t)tap * d.sc_tap + (int64_t)c * d.sc_n;
+      } else {
+        coff = (int64_t)m * d.sc_m + (int64_t)n * d.sc_n;
+      }
+      if (mask) {
+        float mv = load_as_f32(mask, d.dtype_mask, coff);
+        v = (mv != 0.f) ? v * d.mask_scale : 0.f;
+      }
+      if (dr.on) v = drop_apply(dr, ((unsigned long long)bz * d.M + m) * (unsigned long long)d.N + n, v);
+      v *= d.out_scale;
+      if (res) v += res[(int64_t)m * d.sr_m + (int64_t)n * d.sr_n];
+      store_from_f32(C, d.dtype_c, coff, v);
+    }
+  }
+}
+
+int gemm_simt_launch(const A3tGemmDesc* d, const void* A, const void* B, void* C, const float* bias,
+                     const float* res, const void* mask, const unsigned long long* seed,
+                     cudaStream_t st) {
+  dim3 grid(ceil_div(d->N, BN), ceil_div(d->M, BM), d->batch1 * d->batch2);
+  A3T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_simt: grid too large (M=%d batch=%d)", d->M,
+              d->batch1 * d->batch2);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(*d, A, B, C, bias, res, mask, seed);
+  return check_launch("gemm_simt");
+}
+
+// weight packing -------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int N, int C, int taps,
+                                        __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dg) {
+  int64_t total = (int64_t)N * C * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates the fwd layout (n, tap, c) so the fwd store is coalesced
+    int c = i % C;
+    int64_t r = i / C;
+    int tap = r % taps;
+    int n = r / taps;
+    float v = w[((int64_t)n * C + c) * taps + tap];
+    __nv_bfloat16 bv = __float2bfloat16_rn(v);
+    if (fwd) fwd[i] = bv;
+    if (dg) dg[((int64_t)c * taps + (taps - 1 - tap)) * N + n] = bv;
+  }
+}
+
+}  // namespace a3t
+
+extern "C" const char* a3t_last_error(void) { return a3t::g_err; }
+extern "C" int a3t_version(void) { return 100; }
+
+extern "C" int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void* fwd, void* dg, void* stream) {
+  A3T_REQUIRE(w && N > 0 && C > 0 && taps > 0, "pack_conv_weight: bad args");
+  int64_t total = (int64_t)N * C * taps;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  a3t::pack_conv_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, N, C, taps, (__nv_bfloat16*)fwd,
+                                                                       (__nv_bfloat16*)dg);
+  return a3t::check_launch("pack_conv_weight");
+}
