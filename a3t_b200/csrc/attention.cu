@@ -1,0 +1,169 @@
+// Legacy relative-position masked softmax, forward and backward
+// (transformer/attention.py:145-165 rel_shift, :205-207 scale, :79-88 mask/softmax/zero/dropout).
+// One warp per (b,h,i) score row; the row lives in shared memory.
+#include <float.h>
+#include "common.cuh"
+
+namespace a3t {
+
+constexpr int SM_WARPS = 4;
+
+// rel_shift gather: padded view (S, S+1) with a zero first column, reinterpreted as (S+1, S),
+// first row dropped.  shifted[i,j] = padded_flat[(i+1)*S + j].
+__device__ __forceinline__ float bd_shifted(const float* __restrict__ bd, int S, int i, int j) {
+  int64_t f = (int64_t)(i + 1) * S + j;
+  int r = (int)(f / (S + 1));
+  int c = (int)(f - (int64_t)r * (S + 1));
+  return c == 0 ? 0.f : bd[(int64_t)r * S + (c - 1)];
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
+    const float* __restrict__ ac, const float* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
+    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    const unsigned long long* __restrict__ seed, uint32_t site) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* row = sm + (size_t)warp * S;
+  Drop dr = make_drop(drop_p, seed, site);
+  const int64_t nrows = (int64_t)B * H * S;
+  for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
+    const int i = (int)(r % S);
+    const int64_t bh = r / S;
+    const int b = (int)(bh / H);
+    const float* acr = ac + r * S;
+    const float* bdm = bd_raw + bh * (int64_t)S * S;
+    const uint8_t* km = keymask + (int64_t)b * S;
+    float mx = -FLT_MAX;
+    for (int j = lane; j < S; j += 32) {
+      float s = (acr[j] + bd_shifted(bdm, S, i, j)) * scale;
+      if (!km[j]) s = -FLT_MAX;  // finfo(float32).min
+      row[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      float e = expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < S; j += 32) {
+      float p = km[j] ? row[j] * inv : 0.f;
+      P[r * S + j] = from_f32<TP>(p);
+      if (dr.on) Pd[r * S + j] = from_f32<TP>(drop_apply(dr, (unsigned long long)(r * S + j), p));
+      else if (Pd != P) Pd[r * S + j] = from_f32<TP>(p);
+    }
+    __syncwarp();
+  }
+}
+
+// dS[i,j] = P * (dPu - sum_j dPu*P) * scale ; dPu = dPd*keep/(1-p)
+template <typename TP, typename TO>
+__global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
+    const float* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, float scale,
+    float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* row = sm + (size_t)warp * S;
+  Drop dr = make_drop(drop_p, seed, site);
+  for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
+    float dot = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      float g = dPd[r * S + j];
+      if (dr.on) g = drop_keep(dr, (unsigned long long)(r * S + j)) ? g * dr.inv_keep : 0.f;
+      row[j] = g;
+      dot += g * to_f32<TP>(P[r * S + j]);
+    }
+    dot = warp_sum(dot);
+    for (int j = lane; j < S; j += 32) {
+      float p = to_f32<TP>(P[r * S + j]);
+      dS[r * S + j] = from_f32<TO>(p * (row[j] - dot) * scale);
+    }
+    __syncwarp();
+  }
+}
+
+// dBD_raw[r, cc] = dS at the inverse rel_shift position (0 where BD_raw is never read)
+template <typename TO>
+__global__ void __launch_bounds__(256) relshift_bwd_kernel(const TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nmat,
+                                                           int S) {
+  const int64_t per = (int64_t)S * S;
+  const int64_t n = nmat * per;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    int64_t m = idx / per;
+    int64_t e = idx - m * per;
+    int r = (int)(e / S), cc = (int)(e - (int64_t)r * S);
+    int64_t f = (int64_t)r * (S + 1) + cc + 1 - S;  // flat index into the (S,S) shifted matrix
+    dBD[idx] = f >= 0 ? dS[m * per + f] : from_f32<TO>(0.f);
+  }
+}
+
+}  // namespace a3t
+
+using namespace a3t;
+
+extern "C" int a3t_relpos_softmax_fwd(const float* ac, const float* bd_raw, const uint8_t* keymask, void* P, void* Pd,
+                                      int dtype_p, int B, int H, int S, float scale, float drop_p,
+                                      const unsigned long long* seed, uint32_t site, void* stream) {
+  A3T_REQUIRE(ac && bd_raw && keymask && P && Pd, "relpos_softmax_fwd: null pointer");
+  A3T_REQUIRE(drop_p == 0.f || (seed && Pd != P), "relpos_softmax_fwd: dropout needs a seed and a separate Pd");
+  A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_fwd: S=%d out of range", S);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t nrows = (int64_t)B * H * S;
+  int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  size_t smem = (size_t)SM_WARPS * S * sizeof(float);
+  if (dtype_p == A3T_BF16) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(relpos_softmax_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    relpos_softmax_fwd_kernel<__nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
+        ac, bd_raw, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(relpos_softmax_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    relpos_softmax_fwd_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, keymask, (float*)P, (float*)Pd, B,
+                                                                         H, S, scale, drop_p, seed, site);
+  }
+  return check_launch("relpos_softmax_fwd");
+}
+
+template <typename TP, typename TO>
+static int softmax_bwd_launch(const float* dPd, const void* P, void* dS, void* dBD, int B, int H, int S, float scale,
+                              float drop_p, const unsigned long long* seed, uint32_t site, cudaStream_t st) {
+  int64_t nrows = (int64_t)B * H * S;
+  int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  size_t smem = (size_t)SM_WARPS * S * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(relpos_softmax_bwd_kernel<TP, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, (const TP*)P, (TO*)dS, nrows, S, scale,
+                                                                        drop_p, seed, site);
+  int rc = check_launch("relpos_softmax_bwd");
+  if (rc) return rc;
+  int64_t n = nrows * S;
+  int64_t b2 = (n + 255) / 256;
+  if (b2 > 148 * 16) b2 = 148 * 16;
+  relshift_bwd_kernel<TO><<<(int)b2, 256, 0, st>>>((const TO*)dS, (TO*)dBD, (int64_t)B * H, S);
+  return check_launch("relshift_bwd");
+}
+
+extern "C" int a3t_relpos_softmax_bwd(const float* dPd, const void* P, int dtype_p, void* dS, void* dBD, int dtype_o,
+                                      int B, int H, int S, float scale, float drop_p, const unsigned long long* seed,
+                                      uint32_t site, void* stream) {
+  A3T_REQUIRE(dPd && P && dS && dBD, "relpos_softmax_bwd: null pointer");
+  A3T_REQUIRE(drop_p == 0.f || seed, "relpos_softmax_bwd: dropout needs a seed");
+  A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_bwd: S=%d out of range", S);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_p == A3T_BF16 && dtype_o == A3T_BF16)
+    return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+  if (dtype_p == A3T_F32 && dtype_o == A3T_F32)
+    return softmax_bwd_launch<float, float>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+  if (dtype_p == A3T_BF16 && dtype_o == A3T_F32)
+    return softmax_bwd_launch<__nv_bfloat16, float>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+  set_error("relpos_softmax_bwd: unsupported dtype combination");
+  return A3T_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's model classes for the A3T hot path.
+
+Same class names, constructor kwargs, `state_dict` keys/shapes, forward signatures and return
+values as the reference (so `MLMTask.build_model`, published checkpoints and
+`bin/sedit_inference.py` drop in), but `forward` runs the hand-written CUDA path
+(`a3t_b200.graph` over `a3t_b200.backend.CudaBackend`), never torch.nn compute:
+
+  MLMEncoder / MLMDecoder          espnet/nets/pytorch_backend/conformer/encoder.py:279-614
+  ESPnetMLMEncAsDecoderModel       espnet2/tts/sedit/sedit_model.py:47-375
+  Postnet (parameter layout)       espnet/nets/pytorch_backend/tacotron2/decoder.py:150-268
+
+The torch.nn leaf modules below (Linear, Conv1d, LayerNorm, BatchNorm1d, Embedding) are used
+ONLY as parameter containers so that names, shapes and default initialisation match the
+reference; their `forward` is never called.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import graph
+from .graph import A3TConfig, WeightCache
+
+
+class _ParamsOnly(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the CUDA graph in a3t_b200.graph computes this layer")
+
+
+class NewMaskInputLayer(_ParamsOnly):
+    """espnet2/asr/encoder/mlm_encoder.py:57-70"""
+
+    def __init__(self, out_features: int):
+        super().__init__()
+        self.mask_feature = nn.Parameter(torch.empty((1, 1, out_features)).normal_())
+
+
+class _SelfAttn(_ParamsOnly):
+    """LegacyRelPositionMultiHeadedAttention parameters (transformer/attention.py:117-143)."""
+
+    def __init__(self, n_head, n_feat):
+        super().__init__()
+        self.d_k = n_feat // n_head
+        self.h = n_head
+        self.linear_q = nn.Linear(n_feat, n_feat)
+        self.linear_k = nn.Linear(n_feat, n_feat)
+        self.linear_v = nn.Linear(n_feat, n_feat)
+        self.linear_out = nn.Linear(n_feat, n_feat)
+        self.linear_pos = nn.Linear(n_feat, n_feat, bias=False)
+        self.pos_bias_u = nn.Parameter(torch.Tensor(self.h, self.d_k))
+        self.pos_bias_v = nn.Parameter(torch.Tensor(self.h, self.d_k))
+        nn.init.xavier_uniform_(self.pos_bias_u)
+        nn.init.xavier_uniform_(self.pos_bias_v)
+
+
+class _ConvFFN(_ParamsOnly):
+    """MultiLayeredConv1d parameters (transformer/multi_layer_conv.py:33-46)."""
+
+    def __init__(self, in_chans, hidden_chans, kernel_size):
+        super().__init__()
+        self.w_1 = nn.Conv1d(in_chans, hidden_chans, kernel_size, stride=1, padding=(kernel_size - 1) // 2)
+        self.w_2 = nn.Conv1d(hidden_chans, in_chans, kernel_size, stride=1, padding=(kernel_size - 1) // 2)
+
+
+class _ConvModule(_ParamsOnly):
+    """ConvolutionModule parameters (conformer/convolution.py:28-54)."""
+
+    def __init__(self, channels, kernel_size):
+        super().__init__()
+        assert (kernel_size - 1) % 2 == 0
+        self.pointwise_conv1 = nn.Conv1d(channels, 2 * channels, 1)
+        self.depthwise_conv = nn.Conv1d(channels, channels, kernel_size, padding=(kernel_size - 1) // 2,
+                                        groups=channels)
+        self.norm = nn.BatchNorm1d(channels)
+        self.pointwise_conv2 = nn.Conv1d(channels, channels, 1)
+
+
+class _EncoderLayer(_ParamsOnly):
+    """EncoderLayer parameters (conformer/encoder_layer.py:43-78)."""
+
+    def __init__(self, size, heads, linear_units, ffn_kernel, dw_kernel):
+        super().__init__()
+        self.self_attn = _SelfAttn(heads, size)
+        self.feed_forward = _ConvFFN(size, linear_units, ffn_kernel)
+        self.feed_forward_macaron = _ConvFFN(size, linear_units, ffn_kernel)
+        self.conv_module = _ConvModule(size, dw_kernel)
+        self.norm_ff = nn.LayerNorm(size, eps=1e-12)
+        self.norm_mha = nn.LayerNorm(size, eps=1e-12)
+        self.norm_ff_macaron = nn.LayerNorm(size, eps=1e-12)
+        self.norm_conv = nn.LayerNorm(size, eps=1e-12)
+        self.norm_final = nn.LayerNorm(size, eps=1e-12)
+
+
+_UNSUPPORTED = "a3t_b200 builds the shipped A3T configuration only ({}); use the reference class for other options"
+
+
+class MLMEncoder(nn.Module):
+    """Constructor signature of conformer/encoder.py:315-343 (the keys `conf/fsp2_conformer.yaml`
+    splats).  Only the A3T paper topology is built: conv1d macaron FFN, (legacy) rel-pos attention,
+    conv module, pre-norm, sega_mlm / mlm input layer."""
+
+    def __init__(self, idim, vocab_size=0, pre_speech_layer: int = 0, attention_dim=256, attention_heads=4,
+                 linear_units=2048, num_blocks=6, dropout_rate=0.1, positional_dropout_rate=0.1,
+                 attention_dropout_rate=0.0, input_layer="conv2d", normalize_before=True, concat_after=False,
+                 positionwise_layer_type="linear", positionwise_conv_kernel_size=1, macaron_style=False,
+                 pos_enc_layer_type="abs_pos", pos_enc_class=None, selfattention_layer_type="selfattn",
+                 activation_type="swish", use_cnn_module=False, zero_triu=False, cnn_module_kernel=31,
+                 padding_idx=-1, stochastic_depth_rate=0.0, intermediate_layers=None):
+        super().__init__()
+        req = [(normalize_before, "normalize_before=True"), (not concat_after, "concat_after=False"),
+               (positionwise_layer_type == "conv1d", "positionwise_layer_type=conv1d"),
+               (macaron_style, "macaron_style=True"), (use_cnn_module, "use_cnn_module=True"),
+               (pos_enc_layer_type in ("rel_pos", "legacy_rel_pos"), "pos_enc_layer_type=rel_pos"),
+               (selfattention_layer_type in ("rel_selfattn", "legacy_rel_selfattn"), "selfattention_layer_type=rel_selfattn"),
+               (activation_type == "swish", "activation_type=swish"), (not zero_triu, "zero_triu=False"),
+               (pre_speech_layer == 0, "pre_speech_layer=0"), (stochastic_depth_rate == 0.0, "stochastic_depth_rate=0"),
+               (intermediate_layers is None, "intermediate_layers=None"), (padding_idx == -1, "padding_idx=-1")]
+        for ok, what in req:
+            if not ok:
+                raise NotImplementedError(_UNSUPPORTED.format(what))
+        self._output_size = attention_dim
+        self.attention_dim, self.attention_heads, self.linear_units = attention_dim, attention_heads, linear_units
+        self.num_blocks, self.ffn_kernel, self.cnn_module_kernel = num_blocks, positionwise_conv_kernel_size, cnn_module_kernel
+        self.dropout_rate, self.positional_dropout_rate = dropout_rate, positional_dropout_rate
+        self.attention_dropout_rate = attention_dropout_rate
+        self.input_layer = input_layer
+        self.normalize_before = normalize_before
+        self.pre_speech_layer = pre_speech_layer
+        self.intermediate_layers = None
+        self.conv_subsampling_factor = 1
+        if input_layer in ("mlm", "sega_mlm"):
+            self.segment_emb = (nn.Embedding(500, attention_dim, padding_idx=padding_idx)
+                                if input_layer == "sega_mlm" else None)
+            self.speech_embed = nn.Sequential(NewMaskInputLayer(idim), nn.Linear(idim, attention_dim),
+                                              nn.LayerNorm(attention_dim), nn.ReLU(), _ParamsOnly())
+            self.text_embed = nn.Sequential(nn.Embedding(vocab_size, attention_dim, padding_idx=padding_idx),
+                                            _ParamsOnly())
+        elif input_layer is None:
+            self.embed = nn.Sequential(_ParamsOnly())
+        else:
+            raise NotImplementedError(_UNSUPPORTED.format("input_layer in {sega_mlm, mlm, None}"))
+        self.encoders = nn.ModuleList([
+            _EncoderLayer(attention_dim, attention_heads, linear_units, positionwise_conv_kernel_size,
+                          cnn_module_kernel) for _ in range(num_blocks)])
+        self.pre_speech_encoders = nn.ModuleList([])
+        self.after_norm = nn.LayerNorm(attention_dim, eps=1e-12)
+
+    def output_size(self):
+        return self._output_size
+
+    def forward(self, *a, **k):
+        raise RuntimeError("MLMEncoder is executed as part of ESPnetMLMEncAsDecoderModel's fused CUDA graph; "
+                           "call the model, not the encoder")
+
+
+class MLMDecoder(MLMEncoder):
+    """conformer/encoder.py:568-614; built by MLMTask as `decoder_class(idim=0, input_layer=None, **conf)`."""
+
+
+class Postnet(_ParamsOnly):
+    """Parameter layout of tacotron2/decoder.py:150-252 with use_batch_norm=True."""
+
+    def __init__(self, idim, odim, n_layers=5, n_chans=512, n_filts=5, dropout_rate=0.5, use_batch_norm=True):
+        super().__init__()
+        if not use_batch_norm:
+            raise NotImplementedError(_UNSUPPORTED.format("postnet use_batch_norm=True"))
+        self.postnet = nn.ModuleList()
+        for layer in range(n_layers):
+            ichans = odim if layer == 0 else n_chans
+            ochans = odim if layer == n_layers - 1 else n_chans
+            mods = [nn.Conv1d(ichans, ochans, n_filts, stride=1, padding=(n_filts - 1) // 2, bias=False),
+                    nn.BatchNorm1d(ochans)]
+            if layer != n_layers - 1:
+                mods.append(nn.Tanh())
+            mods.append(nn.Dropout(dropout_rate))
+            self.postnet.append(nn.Sequential(*mods))
+        self.dropout_rate = dropout_rate
+
+
+class _A3TFunction(torch.autograd.Function):
+    """loss/before/after = model(batch); hand-written backward over the CUDA backend."""
+
+    @staticmethod
+    def forward(ctx, model, batch, training, need_loss, *params):
+        ops = model._backend(batch["speech"].device)
+        P = model._param_dict()
+        loss, before, after, sctx = graph.forward(ops, P, model._wcache, model.cfg, batch, training, need_loss)
+        ctx.model, ctx.ops, ctx.P, ctx.sctx = model, ops, P, sctx
+        ctx.names = model._param_names
+        outs = (loss if loss is not None else before.new_zeros(1), before, after if after is not None else before)
+        return outs
+
+    @staticmethod
+    def backward(ctx, gloss, gbefore, gafter):
+        model = ctx.model
+        gl = gloss if gloss is not None else torch.zeros(1, device=ctx.sctx.saved["speech"].device)
+        G = graph.backward(ctx.ops, ctx.P, model._wcache, model.cfg, ctx.sctx, gl.float().contiguous(),
+                           dbefore_ext=gbefore, dafter_ext=gafter if ctx.sctx.saved["after"] is not None else None)
+        ctx.sctx = None
+        grads = tuple(G.get(n) for n in ctx.names)
+        return (None, None, None, None) + grads
+
+
+class ESPnetMLMModel(nn.Module):
+    """espnet2/tts/sedit/sedit_model.py:47-340 (constructor signature :48-71)."""
+
+    def __init__(self, token_list: Union[Tuple[str, ...], List[str]], odim: int, feats_extract, normalize,
+                 encoder: nn.Module, decoder: Optional[nn.Module], postnet_layers: int = 0, postnet_chans: int = 0,
+                 postnet_filts: int = 0, ignore_id: int = -1, lsm_weight: float = 0.0,
+                 length_normalized_loss: bool = False, report_cer: bool = True, report_wer: bool = True,
+                 sym_space: str = "<space>", sym_blank: str = "<blank>", masking_schema: str = "span",
+                 mean_phn_span: int = 3, mlm_prob: float = 0.25, dynamic_mlm_prob=False, decoder_seg_pos=False,
+                 act_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        if lsm_weight > 50:
+            raise NotImplementedError(_UNSUPPORTED.format("L1 loss (lsm_weight <= 50)"))
+        if decoder is None:
+            raise NotImplementedError(_UNSUPPORTED.format("a conformer decoder"))
+        self.odim = odim
+        self.ignore_id = ignore_id
+        self.token_list = list(token_list)
+        self.normalize = normalize
+        self.encoder = encoder
+        self.decoder = decoder
+        self.feats_extract = feats_extract
+        self.mlm_weight = 1.0
+        self.mlm_prob = mlm_prob
+        self.mean_phn_span = mean_phn_span
+        self.masking_schema = masking_schema
+        self.decoder_seg_pos = decoder_seg_pos
+        self.sfc = nn.Linear(self.encoder._output_size, odim)
+        self.postnet = (None if postnet_layers == 0 else
+                        Postnet(idim=self.encoder._output_size, odim=odim, n_layers=postnet_layers,
+                                n_chans=postnet_chans, n_filts=postnet_filts, use_batch_norm=True, dropout_rate=0.5))
+        self.act_dtype = act_dtype
+        self._wcache = WeightCache()
+        self._backends: Dict[str, object] = {}
+        self._pd = None
+        self.dropout_seed = 0
+
+    # ---- plumbing --------------------------------------------------------------------------
+    @property
+    def cfg(self) -> A3TConfig:
+        e, d = self.encoder, self.decoder
+        return A3TConfig(
+            idim=e.speech_embed[1].in_features, odim=self.odim, vocab_size=e.text_embed[0].num_embeddings,
+            D=e.attention_dim, H=e.attention_heads, FF=e.linear_units, ffn_kernel=e.ffn_kernel,
+            enc_blocks=e.num_blocks, dec_blocks=d.num_blocks, enc_dw_kernel=e.cnn_module_kernel,
+            dec_dw_kernel=d.cnn_module_kernel, dropout=e.dropout_rate, pos_dropout=e.positional_dropout_rate,
+            att_dropout=e.attention_dropout_rate, dec_dropout=d.dropout_rate,
+            dec_pos_dropout=d.positional_dropout_rate, dec_att_dropout=d.attention_dropout_rate,
+            postnet_layers=0 if self.postnet is None else len(self.postnet.postnet),
+            postnet_chans=0 if self.postnet is None else self.postnet.postnet[0][0].out_channels,
+            postnet_filts=0 if self.postnet is None else self.postnet.postnet[0][0].kernel_size[0],
+            postnet_dropout=0.0 if self.postnet is None else self.postnet.dropout_rate,
+            sega=e.segment_emb is not None)
+
+    def _backend(self, device):
+        from .backend import CudaBackend  # fails loudly without the CUDA library / device
+
+        key = f"{device}|{self.act_dtype}"
+        b = self._backends.get(key)
+        if b is None:
+            b = CudaBackend(device, self.act_dtype, seed=self.dropout_seed)
+            self._backends[key] = b
+        return b
+
+    def _param_dict(self) -> Dict[str, torch.Tensor]:
+        P = {n: p.detach() for n, p in self.named_parameters()}
+        P.update({n: b for n, b in self.named_buffers()})
+        return P
+
+    @property
+    def _param_names(self):
+        return [n for n, _ in self.named_parameters()]
+
+    def _run(self, batch, need_loss=True):
+        params = [p for _, p in self.named_parameters()]
+        return _A3TFunction.apply(self, batch, self.training, need_loss, *params)
+
+    # ---- AbsESPnetModel interface (espnet2/train/abs_espnet_model.py:34-42) ---------------
+    def forward(self, speech, text, masked_position, speech_mask, text_mask, speech_segment_pos, text_segment_pos,
+                y_masks=None, speech_lengths=None, text_lengths=None):
+        batch_size = speech.shape[0]
+        batch = dict(speech=speech, text=text, masked_position=masked_position, speech_mask=speech_mask,
+                     text_mask=text_mask, speech_segment_pos=speech_segment_pos, text_segment_pos=text_segment_pos)
+        loss, before, after = self._run(batch, need_loss=True)
+        if self.training:
+            self._backend(speech.device).advance_seed()
+        stats = dict(loss=loss.detach(), loss_mlm=loss.detach(), loss_copy=None)
+        weight = torch.tensor([batch_size], device=loss.device)  # force_gatherable (torch_utils/device_funcs.py:36)
+        return loss, stats, weight
+
+    def _forward(self, batch, speech_segment_pos=None, y_masks=None):
+        """sedit_model.py:350-375: returns (before_outs, after_outs, speech_pad, masked_position)."""
+        b = dict(speech=batch["speech_pad"], text=batch["text_pad"], masked_position=batch["masked_position"],
+                 speech_mask=batch["speech_mask"], text_mask=batch["text_mask"],
+                 speech_segment_pos=batch["speech_segment_pos"], text_segment_pos=batch["text_segment_pos"])
+        _, before, after = self._run(b, need_loss=False)
+        return before, (after if self.postnet is not None else None), batch["speech_pad"], batch["masked_position"]
+
+    def collect_feats(self, speech, speech_lengths, text, text_lengths, **kwargs):
+        """sedit_model.py:125-128"""
+        if self.feats_extract is not None:
+            feats, feats_lengths = self.feats_extract(speech, speech_lengths)
+        else:
+            feats, feats_lengths = speech, speech_lengths
+        return {"feats": feats, "feats_lengths": feats_lengths}
+
+    def inference(self, speech, text, masked_position, speech_mask, text_mask, speech_segment_pos, text_segment_pos,
+                  span_boundary, y_masks=None, speech_lengths=None, text_lengths=None, feats=None, spembs=None,
+                  sids=None, lids=None, threshold: float = 0.5, minlenratio: float = 0.0, maxlenratio: float = 10.0,
+                  use_teacher_forcing: bool = False):
+        """sedit_model.py:239-284: single-pass infill; output list [orig[:s], generated[s:e], orig[e:]]."""
+        if not use_teacher_forcing:
+            raise NotImplementedError("the reference's use_teacher_forcing=False branch is dead code "
+                                      "(sedit_model.py:286-317 references undefined names)")
+        batch = dict(speech_pad=speech, text_pad=text, masked_position=masked_position, speech_mask=speech_mask,
+                     text_mask=text_mask, speech_segment_pos=speech_segment_pos, text_segment_pos=text_segment_pos)
+        outs = [speech[:, :span_boundary[0]]]
+        with torch.no_grad():
+            before, zs, _, _ = self._forward(batch, speech_segment_pos, y_masks=y_masks)
+        if zs is None:
+            zs = before
+        outs += [zs[0][span_boundary[0]:span_boundary[1]]]
+        outs += [speech[:, span_boundary[1]:]]
+        return dict(feat_gen=outs)
+
+
+class ESPnetMLMEncAsDecoderModel(ESPnetMLMModel):
+    """espnet2/tts/sedit/sedit_model.py:348-375 (the paper model)."""
+
+
+def initialize_xavier_uniform(model: nn.Module):
+    """espnet2/torch_utils/initialize.py:63-88 with init='xavier_uniform': xavier on dim>1 params,
+    zero every 1-D param, then reset Embedding / LayerNorm modules."""
+    for p in model.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_uniform_(p.data)
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.zero_()
+    for m in model.modules():
+        if isinstance(m, (nn.Embedding, nn.LayerNorm)):
+            m.reset_parameters()
+
+
+def build_model(encoder_conf: dict, decoder_conf: dict, model_conf: dict, vocab_size: int = 73, idim: int = 80,
+                odim: int = 80, feats_extract=None, init: Optional[str] = "xavier_uniform",
+                act_dtype: torch.dtype = torch.float32) -> ESPnetMLMEncAsDecoderModel:
+    """What `MLMTask.build_model` (espnet2/tasks/mlm.py:329-443) does for encoder=decoder=conformer."""
+    token_list = ["<blank>", "<unk>"] + [f"p{i}" for i in range(vocab_size - 3)] + ["<sos/eos>"]
+    enc = MLMEncoder(idim, vocab_size=vocab_size, pos_enc_class=None, **encoder_conf)
+    dec = MLMDecoder(idim=0, input_layer=None, **decoder_conf)
+    model = ESPnetMLMEncAsDecoderModel(feats_extract=feats_extract, odim=odim, normalize=None, encoder=enc,
+                                       decoder=dec, token_list=token_list, act_dtype=act_dtype, **model_conf)
+    if init is not None:
+        initialize_xavier_uniform(model)
+    return model

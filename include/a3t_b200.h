@@ -193,11 +193,12 @@ int a3t_bn_act_bwd(const float* dy, const float* z, const float* mean, const flo
 
 /* Masked L1 (espnet2/tts/sedit/sedit_model.py:320-340):
  * loss = sum_rows mask*(|before-y|_1 + |after-y|_1) / (sum mask + 1e-10).  out[0]=loss, out[1]=den.
- * partial = 2*nblk doubles, nblk = a3t_colsum_blocks(rows). */
+ * partial = 2*nblk doubles, nblk = a3t_colsum_blocks(rows).  `after`/`dafter` may be NULL (no
+ * postnet).  bwd: d before = gloss/den * mask * sign(before-y) (same for after); den = &out[1]. */
 int a3t_masked_l1_fwd(const float* before, const float* after, const float* y, const uint8_t* mask,
                       float* out, double* partial, int64_t rows, int C, void* stream);
 int a3t_masked_l1_bwd(const float* gloss, const float* before, const float* after, const float* y,
-                      const uint8_t* mask, const float* out, float* dbefore, float* dafter,
+                      const uint8_t* mask, const float* den, float* dbefore, float* dafter,
                       int64_t rows, int C, void* stream);
 
 /* Trainer glue (espnet2/train/trainer.py:631-675; schedulers/noam_lr.py:58-65): squared L2 norm of
@@ -217,11 +218,13 @@ int a3t_seed_advance(unsigned long long* seed, void* stream);
  * layers/log_mel.py:56-83): reflect-pad n_fft/2, frame n_fft @ hop, periodic Hann(win_length)
  * centred in n_fft, |rFFT|, sqrt(max(.,1e-10)), @ melmat (n_fft/2+1, n_mels), max(.,1e-10), log10,
  * frames >= olens[b] zeroed.  wav (B,N) fp32, ilens (B) int64, window (win_length) fp32,
- * mel (B,T,n_mels) fp32 with T = 1 + N / hop, olens (B) int64.  n_fft must be a power of two
- * in [256, 4096]. */
+ * mel (B,T,n_mels) fp32 with T = 1 + N / hop, olens (B) int64 (may be NULL).  n_fft must be a
+ * power of two in [256, 4096].  mel_range (optional, 2*n_mels int32): [lo,hi) bin range outside
+ * which column m of melmat is exactly zero (the filters are triangles); NULL = dense.
+ * ilens NULL = every utterance is N samples long. */
 int a3t_stft_logmel(const float* wav, const int64_t* ilens, const float* window, const float* melmat,
-                    float* mel, int64_t* olens, int B, int64_t N, int n_fft, int win_length,
-                    int hop, int n_mels, void* stream);
+                    const int32_t* mel_range, float* mel, int64_t* olens, int B, int64_t N, int n_fft,
+                    int win_length, int hop, int n_mels, void* stream);
 
 /* Collate integer math on device (espnet2/train/collate_fn.py:236-237, :330-343, :346-385). */
 int a3t_align_to_frames(const float* t_sec, int32_t* frames, int64_t n, float fs, float hop,
@@ -247,13 +250,15 @@ int a3t_pwg_upsample(const float* in, const float* w, float* out, int rows, int6
 int a3t_pwg_conv1d(const float* in, const float* w, const float* bias, float* out, int B, int Cin,
                    int Cout, int64_t T, int K, int dil, int pad_mode, int relu_in, float in_scale,
                    void* stream);
-/* one gated residual block, fused: h = dilconv3(x) + bias + aux1x1(c); g = tanh(h[:R])*sigmoid(h[R:]);
+/* one gated residual block, fused: h = dilconv3(x) + bias + aux1x1(c); g = tanh(h[:G/2])*sigmoid(h[G/2:]);
  * o = out1x1(g)+bias; x_out = (o[:R]+x)*sqrt(.5); skip += o[R:]  (skip = o[R:] if first).
- * x,c,skip (B, ch, T); R = residual channels (64), G = gate channels (128), A = aux channels (80). */
-int a3t_pwg_resblock(const float* x, const float* c, const float* w_conv, const float* b_conv,
-                     const float* w_aux, const float* w_out, const float* b_out, float* x_out,
-                     float* skip, int B, int64_t T, int R, int G, int A, int S_, int dil, int first,
-                     void* stream);
+ * x,x_out (B,R,T), c (B,A,T), skip (B,S_,T); x_out must not alias x.
+ * Weights are passed K-major (transposed once at load time by the host):
+ *   w_in_t  (3*R + A, G): row tap*R+i = conv.weight[:, i, tap], row 3*R+a = conv1x1_aux.weight[:, a, 0]
+ *   b_in (G) = conv.bias;   w_out_t (G/2, R+S_): row i = conv1x1_out.weight[:, i, 0];   b_out (R+S_). */
+int a3t_pwg_resblock(const float* x, const float* c, const float* w_in_t, const float* b_in,
+                     const float* w_out_t, const float* b_out, float* x_out, float* skip, int B,
+                     int64_t T, int R, int G, int A, int S_, int dil, int first, void* stream);
 
 #ifdef __cplusplus
 }
