@@ -77,7 +77,7 @@ _SIGS = {
     "a3t_masked_l1_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "a3t_masked_l1_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "a3t_grad_sqnorm": [_P, _L, _P, _P, _P],
-    "a3t_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _F, _F, _P],
+    "a3t_adam_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "a3t_seed_advance": [_P, _P],
     "a3t_stft_logmel": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P],
     "a3t_align_to_frames": [_P, _P, _L, _F, _F, _P],

@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    const double* __restrict__ sq, const int64_t* __restrict__ step_p,
                                                    float base_lr, float model_size, float warmup, float beta1,
-                                                   float beta2, float eps, float max_norm, float grad_scale) {
+                                                   float beta2, float eps, float max_norm, float grad_scale,
+                                                   const float* __restrict__ denom) {
+  if (denom) grad_scale /= denom[0];
   // total norm of the scaled gradient
   const double norm = sqrt(sq[0]) * (double)grad_scale;
   if (!isfinite(norm)) return;  // trainer.py:640-656: skip the update
@@ -137,7 +139,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     p[i] = p[i] - step_size * (mi / denom);
   }
 }
-__global__ void step_advance_kernel(const double* __restrict__ sq, int64_t* __restrict__ step_p, float grad_scale) {
+__global__ void step_advance_kernel(const double* __restrict__ sq, int64_t* __restrict__ step_p, float grad_scale,
+                                    const float* __restrict__ denom) {
+  if (denom) grad_scale /= denom[0];
   const double norm = sqrt(sq[0]) * (double)grad_scale;
   if (isfinite(norm)) step_p[0] += 1;
 }
@@ -187,17 +191,17 @@ extern "C" int a3t_grad_sqnorm(const float* g, int64_t n, double* sq, double* pa
 
 extern "C" int a3t_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sq, int64_t* step,
                              float base_lr, float model_size, float warmup, float beta1, float beta2, float eps,
-                             float max_norm, float grad_scale, void* stream) {
+                             float max_norm, float grad_scale, const float* denom, void* stream) {
   A3T_REQUIRE(p && g && m && v && sq && step, "adam_step: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t b = (n + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
   adam_kernel<<<(int)b, 256, 0, st>>>(p, g, m, v, n, sq, step, base_lr, model_size, warmup, beta1, beta2, eps,
-                                      max_norm, grad_scale);
+                                      max_norm, grad_scale, denom);
   int rc = check_launch("adam_step");
   if (rc) return rc;
-  step_advance_kernel<<<1, 1, 0, st>>>(sq, step, grad_scale);
+  step_advance_kernel<<<1, 1, 0, st>>>(sq, step, grad_scale, denom);
   return check_launch("adam_step_advance");
 }
 

@@ -1,0 +1,83 @@
+"""Data-parallel training step for the A3T model: one process per GPU, ONE NCCL all-reduce.
+
+Replaces the reference's trainer glue for this path (espnet2/train/trainer.py:243-275 DDP wrap,
+:583-597 loss weighting, :631-675 clip / Adam / Noam):
+  * every parameter is a view into one flat fp32 buffer; gradients into a second flat buffer
+    whose 4-float tail carries the statistics the reference all-reduces separately
+    (sum loss*B, sum loss_mlm*B, sum B, stop flag) -> a single in-place all-reduce per step;
+  * gradient = sum_r(loss_r * B_r) / sum_r B_r, as trainer.py:583-595 + DDP mean produce;
+  * clip_grad_norm_(max_norm) + Adam + NoamLR fused in one kernel pass (`a3t_adam_step`), with the
+    non-finite-norm skip of trainer.py:640-656 decided on the device (no host sync);
+  * BatchNorm running statistics stay rank-local (the reference has no SyncBN).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, graph
+
+
+class DataParallelTrainer:
+    def __init__(self, model, lr: float = 1.0, warmup: float = 4000.0, model_size: Optional[float] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.lr, self.warmup, self.betas, self.eps, self.max_norm = lr, warmup, betas, eps, max_norm
+        self.model_size = float(model_size if model_size is not None else model.encoder.attention_dim)
+        params = [(n, p) for n, p in model.named_parameters()]
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise _lib.A3TError("DataParallelTrainer needs the model on a CUDA device")
+        self.device = dev
+        self.names = [n for n, _ in params]
+        sizes = [p.numel() for _, p in params]
+        self.n = sum(sizes)
+        self.flat_p = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n + 4, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.gviews: Dict[str, torch.Tensor] = {}
+        off = 0
+        for (n, p), sz in zip(params, sizes):
+            self.flat_p[off:off + sz].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + sz].view(p.shape)
+            self.gviews[n] = self.flat_g[off:off + sz].view(p.shape)
+            off += sz
+        if self.world > 1:  # C2: one parameter broadcast at init (trainer.py:250-265)
+            dist.broadcast(self.flat_p, 0, group=self.pg)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.sq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.sq_partial = torch.zeros(1024, dtype=torch.float64, device=dev)
+        self.ops = model._backend(dev)
+        self.stats = self.flat_g[self.n:]
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One optimizer step on this rank's shard of the global batch.  Returns the device tensor
+        [sum loss*B, sum loss_mlm*B, sum B, stop] (all-reduced); no host synchronisation."""
+        m = self.model
+        ops, cfg, wc = self.ops, m.cfg, m._wcache
+        P = m._param_dict()
+        B = batch["speech"].shape[0]
+        loss, before, after, ctx = graph.forward(ops, P, wc, cfg, batch, True, True)
+        gloss = torch.full((1,), float(B), dtype=torch.float32, device=self.device)
+        G = graph.backward(ops, P, wc, cfg, ctx, gloss)
+        torch._foreach_copy_([self.gviews[n] for n in self.names], [G[n].view(self.gviews[n].shape) for n in self.names])
+        self.stats[0:1] = loss * float(B)
+        self.stats[1:2] = loss * float(B)
+        self.stats[2] = float(B)
+        self.stats[3] = 0.0
+        if self.world > 1:  # C3 (+C5/C6 piggy-backed): the single collective of the step
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("a3t_grad_sqnorm", self.flat_g.data_ptr(), self.n, self.sq.data_ptr(), self.sq_partial.data_ptr(), st)
+        _lib.call("a3t_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                  self.flat_v.data_ptr(), self.n, self.sq.data_ptr(), self.step_count.data_ptr(), self.lr,
+                  self.model_size, self.warmup, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
+                  self.stats[2:3].data_ptr(), st)
+        wc.clear()  # parameters changed under the packed bf16 copies
+        ops.advance_seed()
+        return self.stats

@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the A3T masked-mel training hot path (BASELINE.json metric: mel-frames/s of training).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+A "step" = forward + backward + gradient all-reduce + clip/Adam/Noam of `ESPnetMLMEncAsDecoderModel`
+on one synthetic batch per GPU.  Workload = BASELINE configs[1] ("cfg2"): the VCTK paper Conformer
+(conf/fsp2_conformer.yaml), bf16 GEMM operands, B=16 utterances x Ts=1024 mel frames + Tt=128 phones
+per GPU; frames counted = B*Ts.  Weak scaling for N>1 (per-GPU batch fixed, one NCCL all-reduce).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def paper_conf():
+    """Values of egs2/vctk/sedit/conf/fsp2_conformer.yaml:27-75 (encoder_conf, decoder_conf, model_conf)."""
+    common = dict(attention_dim=384, attention_heads=2, linear_units=1536, num_blocks=4, dropout_rate=0.2,
+                  positional_dropout_rate=0.2, attention_dropout_rate=0.2, macaron_style=True, use_cnn_module=True,
+                  selfattention_layer_type="rel_selfattn", activation_type="swish", pos_enc_layer_type="rel_pos",
+                  positionwise_layer_type="conv1d", positionwise_conv_kernel_size=3)
+    enc = dict(common, input_layer="sega_mlm", pre_speech_layer=0, cnn_module_kernel=7, normalize_before=True)
+    dec = dict(common, cnn_module_kernel=31)
+    mc = dict(lsm_weight=0.1, length_normalized_loss=False, masking_schema="phn_span", mean_phn_span=8, mlm_prob=0.8,
+              dynamic_mlm_prob=False, postnet_layers=5, postnet_filts=5, postnet_chans=256)
+    return enc, dec, mc
+
+
+def synthetic_batch_host(B, Ts, Tt, vocab=73, seed=0, mlm_prob=0.8, mean_phn_span=8):
+    """SURVEY 8d synthetic inputs on the HOST (numpy/torch CPU): random phoneme ids, randn mel, even
+    phone/frame alignment, T5 span mask drawn from np.random like the reference's collate."""
+    from a3t_b200.collate import draw_phone_masks
+
+    g = torch.Generator().manual_seed(seed)
+    np.random.seed(seed)
+    speech = torch.randn(B, Ts, 80, generator=g)
+    text = torch.randint(2, vocab - 1, (B, Tt), generator=g)
+    edges = torch.floor(torch.linspace(0, Ts, Tt + 1)).int()
+    a_s = edges[:-1].unsqueeze(0).repeat(B, 1).contiguous()
+    a_e = edges[1:].unsqueeze(0).repeat(B, 1).contiguous()
+    lens = torch.full((B,), Tt, dtype=torch.int64)
+    pm = torch.from_numpy(draw_phone_masks(lens.tolist(), mlm_prob, mean_phn_span, Tt))
+    return dict(speech=speech, text=text, align_start=a_s, align_end=a_e, align_lengths=lens, phone_mask=pm,
+                speech_mask=torch.ones(B, 1, Ts, dtype=torch.bool), text_mask=torch.ones(B, 1, Tt, dtype=torch.bool))
+
+
+def expand_on_host(h):
+    """masked_position / segment ids with the oracle's integer routines (CPU reference arm only)."""
+    from oracle import a3t_oracle as O
+
+    B, Ts = h["speech"].shape[:2]
+    Tt = h["text"].shape[1]
+    mp = O.expand_phone_mask(h["phone_mask"].numpy(), h["align_start"], h["align_end"], h["align_lengths"],
+                             h["speech_mask"].reshape(B, Ts))
+    sseg, tseg = O.segment_pos(h["align_start"], h["align_end"], h["align_lengths"], Ts, Tt)
+    return dict(speech=h["speech"], text=h["text"], masked_position=mp, speech_mask=h["speech_mask"],
+                text_mask=h["text_mask"], speech_segment_pos=sseg, text_segment_pos=tseg)
+
+
+def device_batch(h, device):
+    """Host batch -> device batch; the span expansion and segment ids run as CUDA kernels."""
+    from a3t_b200 import _lib
+
+    d = {k: v.to(device, non_blocking=True) for k, v in h.items()}
+    B, Ts = d["speech"].shape[:2]
+    Tt = d["text"].shape[1]
+    st = torch.cuda.current_stream(device).cuda_stream
+    mp = torch.empty(B, Ts, dtype=torch.uint8, device=device)
+    valid = d["speech_mask"].reshape(B, Ts).view(torch.uint8)
+    _lib.call("a3t_expand_phone_mask", d["phone_mask"].data_ptr(), d["align_start"].data_ptr(),
+              d["align_end"].data_ptr(), d["align_lengths"].data_ptr(), valid.data_ptr(), mp.data_ptr(), B, Ts, Tt, st)
+    sseg = torch.empty(B, Ts, dtype=torch.int64, device=device)
+    tseg = torch.empty(B, Tt, dtype=torch.int64, device=device)
+    _lib.call("a3t_segment_pos", d["align_start"].data_ptr(), d["align_end"].data_ptr(), d["align_lengths"].data_ptr(),
+              sseg.data_ptr(), tseg.data_ptr(), B, Ts, Tt, st)
+    return dict(speech=d["speech"], text=d["text"], masked_position=mp.view(torch.bool), speech_mask=d["speech_mask"],
+                text_mask=d["text_mask"], speech_segment_pos=sseg, text_segment_pos=tseg)
+
+
+def synthetic_batch(B, Ts, Tt, device="cuda", seed=0):
+    return device_batch(synthetic_batch_host(B, Ts, Tt, seed=seed), torch.device(device))
+
+
+# ---- algorithmic FLOPs -----------------------------------------------------------
+def fwd_flops_per_sample(Ts, Tt, D=384, FF=1536, k=3, enc_dw=7, dec_dw=31, blocks=(4, 4), postnet=(5, 256, 5), mel=80):
+    S = Ts + Tt
+    per_block = lambda kdw: (2 * (2 * S * (k * D) * FF + 2 * S * (k * FF) * D) + 4 * 2 * S * D * D + 3 * 2 * S * S * D
+                             + 2 * S * D * 2 * D + 2 * S * D * kdw + 2 * S * D * D)
+    f = blocks[0] * per_block(enc_dw) + blocks[1] * per_block(dec_dw)
+    f += 2 * Ts * mel * D + 2 * Ts * D * mel
+    n, ch, kf = postnet
+    f += 2 * Ts * kf * (mel * ch + (n - 2) * ch * ch + ch * mel)
+    return f
+
+
+# ---- clocks -----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# kernels launched by one C-ABI call (for gpu_launches)
+KERNELS_PER_CALL = {"a3t_layernorm_bwd": 2, "a3t_colsum": 2, "a3t_mask_input_bwd": 2, "a3t_bn_stats": 2,
+                    "a3t_bn_act_bwd": 3, "a3t_glu_dwconv_bwd": 2, "a3t_masked_l1_fwd": 2, "a3t_grad_sqnorm": 2,
+                    "a3t_adam_step": 2, "a3t_relpos_softmax_bwd": 2, "a3t_stft_logmel": 2}
+
+
+def _count_launches(fn):
+    """Run fn() once counting kernel launches and GEMM calls issued through the C-ABI."""
+    from a3t_b200 import _lib
+
+    counts = {"kernels": 0, "gemm": 0}
+    orig = _lib.call
+
+    def counting(name, *a):
+        rc = orig(name, *a)
+        if name not in _lib._PLAIN_INT:
+            counts["kernels"] += KERNELS_PER_CALL.get(name, 1)
+            if name == "a3t_gemm":
+                counts["gemm"] += 1
+        return rc
+
+    import a3t_b200.backend as bk
+    import a3t_b200.trainer as tr
+
+    _lib.call = bk.call = counting
+    tr._lib.call = counting
+    try:
+        out = fn()
+    finally:
+        _lib.call = bk.call = orig
+        tr._lib.call = orig
+    return out, counts
+
+
+def _time_gemms(fn):
+    """One eager step with a CUDA-event pair around every a3t_gemm call (on the launching stream):
+    returns (total GEMM ms, total tensor-core-eligible GEMM FLOPs, n calls)."""
+    from a3t_b200 import _lib
+    import a3t_b200.backend as bk
+
+    orig = _lib.call
+    evs = []
+
+    def timing(name, *a):
+        if name != "a3t_gemm":
+            return orig(name, *a)
+        d = a[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = orig(name, *a)
+        e1.record()
+        evs.append((e0, e1, 2.0 * d.M * d.N * d.K * d.batch1 * d.batch2))
+        return rc
+
+    _lib.call = bk.call = timing
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = bk.call = orig
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
+    return ms, sum(f for _, _, f in evs), len(evs)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's path (same op graph, torch CPU fp32, autograd backward),
+    on all host threads, on a bounded sample of the cfg2 workload."""
+    from a3t_b200 import graph
+    from a3t_b200.model import build_model
+    from oracle.oracle_backend import OracleBackend
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    enc, dec, mc = paper_conf()
+    torch.manual_seed(0)
+    m = build_model(enc, dec, mc)
+    Bs = args.cpu_batch
+    hb = expand_on_host(synthetic_batch_host(Bs, args.frames, args.phones, seed=0))
+    ops = OracleBackend(seed=1, autograd=True)
+    P = {n: p for n, p in m.named_parameters()}
+    P.update({n: b for n, b in m.named_buffers()})
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        loss, _, _, _ = graph.forward(ops, P, graph.WeightCache(), m.cfg, hb, True, True)
+        loss.backward()
+        return float(loss)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = Bs * args.frames * args.steps / dt
+    sample = f"B={Bs} of {args.batch} utterances x Ts={args.frames}/Tt={args.phones}, {args.steps} step(s), fwd+bwd, fp32, dropout on"
+    print(json.dumps({
+        "impl": "reference", "metric": "mel-frames/sec training (VCTK A3T Conformer cfg2)", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: VCTK paper Conformer 4+4 blocks D=384, Ts=1024, Tt=128 (CPU sample)", "batch": Bs},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_leg(args):
+    """Bounded CPU sample on rank 0 (reported beside the GPU number)."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-batch", str(args.cpu_batch), "--frames", str(args.frames), "--phones", str(args.phones)],
+                       capture_output=True, text=True, timeout=900)
+    for line in r.stdout.strip().splitlines()[::-1]:
+        try:
+            return json.loads(line)["cpu_baseline"]
+        except Exception:
+            continue
+    return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="a3t_b200", choices=["a3t_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--phones", type=int, default=128)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from a3t_b200 import _lib
+    from a3t_b200.model import build_model
+    from a3t_b200.trainer import DataParallelTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    enc, dec, mc = paper_conf()
+    torch.manual_seed(0)
+    act = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model = build_model(enc, dec, mc, act_dtype=act).to(dev).train()
+    with torch.no_grad():  # xavier init zeroes BatchNorm gamma: give the conv module / postnet real work
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and n.endswith("weight"):
+                p.fill_(1.0)
+    trainer = DataParallelTrainer(model)
+    B, Ts, Tt = args.batch, args.frames, args.phones
+    host = synthetic_batch_host(B, Ts, Tt, seed=rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    static = device_batch(pinned, dev)
+    torch.cuda.synchronize()
+
+    # ---- warm-up (eager), then capture the step in a CUDA graph -------------------------------
+    _, counts = _count_launches(lambda: trainer.step(static))
+    for _ in range(W - 1):
+        trainer.step(static)
+    torch.cuda.synchronize()
+    graph_obj, used_graph, graph_err = None, False, None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                trainer.step(static)
+                graph_obj = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_obj, stream=side):
+                    stats_out = trainer.step(static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph_obj.replay()
+            torch.cuda.synchronize()
+            used_graph = True
+        except Exception as e:  # report, then measure eagerly
+            graph_err = repr(e)[:200]
+            graph_obj = None
+            torch.cuda.synchronize()
+
+    def one_step():
+        if used_graph:
+            graph_obj.replay()
+        else:
+            trainer.step(static)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-timed, max over ranks -----------------------------------
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    frames = world * B * Ts * args.steps
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: host (pinned) buffers in, loss out, through the public trainer API ---------------
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fresh = device_batch(pinned, dev)
+        for k, v in fresh.items():
+            static[k].copy_(v)
+        one_step()
+        stats_host = trainer.stats.to("cpu", non_blocking=False)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames / (float(t) / 1e3)
+    loss_now = float(stats_host[0] / stats_host[2])
+
+    # ---- roofline of the dominant kernel (GEMM) from one instrumented eager step ---------------
+    gemm_ms, gemm_flops, n_gemm = _time_gemms(lambda: trainer.step(static))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    alg_flops_step = 3.0 * B * fwd_flops_per_sample(Ts, Tt)
+
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_baseline_leg(args)
+        out = {
+            "metric": "mel-frames/sec training (VCTK A3T Conformer cfg2)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "cfg2: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
+                                   f"B={B}/GPU, Ts={Ts}, Tt={Tt}, train step fwd+bwd+allreduce+clip/Adam/Noam, dropout on",
+                       "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": used_graph,
+                       "graph_error": graph_err, "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
+                       "loss": loss_now, "alg_tflop_per_step_per_gpu": alg_flops_step / 1e12,
+                       "step_tensor_frac_of_peak": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / peak},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "a3t_gemm (all dense contractions of the step)", "launches": n_gemm,
+                         "how": "CUDA-event pair around every a3t_gemm call of one eager step; FLOPs = 2*M*N*K*batch per call",
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "gpu_launches": counts["kernels"] * args.steps, "clocks": clk,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

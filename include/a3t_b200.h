@@ -89,6 +89,10 @@ typedef struct A3tGemmDesc {
 int a3t_gemm(const A3tGemmDesc* d, const void* A, const void* B, void* C, const float* bias,
              const float* res, const void* mask, const unsigned long long* seed, void* stream);
 
+/* 1 if a3t_gemm would run this problem on the tcgen05 tensor-core kernel (shape, dtype, stride and
+ * alignment rules of gemm_tc.cu), 0 if it would take the CUDA-core kernel.  No launch. */
+int a3t_gemm_tc_supported(const A3tGemmDesc* d, const void* A, const void* B, void* C);
+
 /* Pack an fp32 conv/linear weight (N, C, taps) into bf16 K-major operands for the tensor-core
  * kernels: fwd[n, tap*C + c] = w[n,c,tap];  dgrad[c, tap'*N + n] = w[n,c,taps-1-tap'] (either may
  * be NULL).  Weight layout: multi_layer_conv.py:33-46 (torch Conv1d). */
@@ -205,12 +209,14 @@ int a3t_masked_l1_bwd(const float* gloss, const float* before, const float* afte
  * a flat fp32 gradient buffer (sq[0], double; partial = nblk doubles with nblk = 1024), then
  * clip_grad_norm_(max_norm) + Adam + Noam LR in one pass.  `step` is a device int64 holding the
  * number of optimizer steps done so far (incremented by the kernel unless the norm is non-finite,
- * in which case the update is skipped, trainer.py:640-656).  `world` divides the gradient
- * (DDP mean). */
+ * in which case the update is skipped, trainer.py:640-656).  The gradient is multiplied by
+ * grad_scale and, when `denom` (device float, may be NULL) is given, divided by denom[0] — the
+ * all-reduced sum of per-rank batch weights (trainer.py:583-595 + DDP mean).  warmup <= 0 = constant lr. */
 int a3t_grad_sqnorm(const float* g, int64_t n, double* sq, double* partial, void* stream);
 int a3t_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sq,
                   int64_t* step, float base_lr, float model_size, float warmup, float beta1,
-                  float beta2, float eps, float max_norm, float grad_scale, void* stream);
+                  float beta2, float eps, float max_norm, float grad_scale, const float* denom,
+                  void* stream);
 /* advance a device-resident dropout seed: *seed = *seed * 6364136223846793005 + 1442695040888963407 */
 int a3t_seed_advance(unsigned long long* seed, void* stream);
 

@@ -30,10 +30,13 @@ def _vjp(fn, inputs, gout):
 
 
 class OracleBackend:
-    def __init__(self, act_dtype=torch.float32, seed: int = 0):
+    def __init__(self, act_dtype=torch.float32, seed: int = 0, autograd: bool = False):
+        """autograd=True keeps the torch graph through the forward ops so that `loss.backward()` gives the
+        gradients (the CPU-baseline arm of bench.py times exactly that: forward ops + torch autograd)."""
         assert act_dtype == torch.float32, "the oracle computes in fp32"
         self.act_dtype = act_dtype
         self.seed = seed
+        self.autograd = autograd
 
     def set_seed(self, seed):
         self.seed = seed
@@ -43,7 +46,8 @@ class OracleBackend:
 
     # conv family -----------------------------------------------------------------------------
     def pack_weight(self, w):
-        return _PW((w if w.dim() == 3 else w.unsqueeze(-1)).detach())
+        w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+        return _PW(w3 if self.autograd else w3.detach())
 
     def conv_fwd(self, x, pw, bias=None, *, relu=False, drop=None, residual=None, out_scale=1.0, out_dtype=None):
         return O.conv_fwd(x, pw.w, bias, relu=relu, drop=self._d(drop), residual=residual, out_scale=out_scale)

@@ -1,0 +1,237 @@
+"""Every CUDA op of the C-ABI against the CPU oracle on the same seeded inputs (-m gpu).
+fp32 mode: tight tolerances; index/mask/dropout-pattern work: bit-exact."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import a3t_oracle as O
+from oracle.oracle_backend import OracleBackend
+
+
+@pytest.fixture(scope="module")
+def be(cuda_lib):
+    from a3t_b200.backend import CudaBackend
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return CudaBackend("cuda:0", torch.float32, seed=123456789012345)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    return OracleBackend(seed=123456789012345)
+
+
+def g(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def close(a, b, atol=1e-4, rtol=1e-4):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert torch.allclose(a, b, atol=atol, rtol=rtol), f"max err {err}"
+
+
+@pytest.mark.parametrize("taps,C,N,S", [(1, 80, 48, 37), (3, 48, 96, 37), (5, 80, 24, 20), (3, 96, 48, 64)])
+def test_conv_family(be, ob, taps, C, N, S):
+    B = 3
+    x, w, bias, res = g(B, S, C, seed=1), g(N, C, taps, seed=2, scale=0.1), g(N, seed=3), g(B, S, N, seed=4)
+    pw_o, pw_c = ob.pack_weight(w), be.pack_weight(w.cuda())
+    for kw in (dict(), dict(relu=True, drop=(0.25, 7)), dict(drop=(0.5, 9), residual=True, out_scale=0.5)):
+        kwo, kwc = dict(kw), dict(kw)
+        if kw.get("residual"):
+            kwo["residual"], kwc["residual"] = res, res.cuda()
+        yo = ob.conv_fwd(x, pw_o, bias, **kwo)
+        yc = be.conv_fwd(x.cuda(), pw_c, bias.cuda(), **kwc)
+        close(yc, yo)
+        if "drop" in kw and not kw.get("residual"):  # dropout pattern is bit-identical
+            assert torch.equal(yc.cpu() == 0, yo == 0)
+    dy = g(B, S, N, seed=5)
+    mask = (g(B, S, C, seed=6) > 0).float() * 1.25
+    close(be.conv_dgrad(dy.cuda(), pw_c), ob.conv_dgrad(dy, pw_o))
+    close(be.conv_dgrad(dy.cuda(), pw_c, mask=mask.cuda(), mask_scale=1.25), ob.conv_dgrad(dy, pw_o, mask=mask, mask_scale=1.25))
+    close(be.conv_wgrad(dy.cuda(), x.cuda(), taps), ob.conv_wgrad(dy, x, taps), atol=2e-4)
+    close(be.colsum(dy.cuda()), ob.colsum(dy), atol=2e-4)
+
+
+@pytest.mark.parametrize("C,rows", [(384, 77), (128, 5), (32, 300), (16, 9)])
+def test_layernorm(be, ob, C, rows):
+    x, gam, bet, dy, dres = g(3, rows, C, seed=1, scale=2.0), 1 + 0.2 * g(C, seed=2), 0.1 * g(C, seed=3), g(3, rows, C, seed=4), g(3, rows, C, seed=5)
+    for kw in (dict(), dict(relu=True, out_scale=math.sqrt(C)), dict(drop=(0.2, 3))):
+        for eps in (1e-12, 1e-5):
+            yo, mo, ro = ob.ln_fwd(x, gam, bet, eps, **kw)
+            yc, mc, rc = be.ln_fwd(x.cuda(), gam.cuda(), bet.cuda(), eps, **kw)
+            close(yc, yo, atol=2e-4)
+            close(mc, mo, atol=1e-5)
+            close(rc, ro, rtol=1e-4)
+            dxo, dgo, dbo = ob.ln_bwd(dy, x, mo, ro, gam, bet, dres=dres, eps=eps, **kw)
+            dxc, dgc, dbc = be.ln_bwd(dy.cuda(), x.cuda(), mc, rc, gam.cuda(), bet.cuda(), dres=dres.cuda(), eps=eps, **kw)
+            close(dxc, dxo, atol=5e-4, rtol=1e-3)
+            close(dgc, dgo, atol=2e-3, rtol=1e-3)
+            close(dbc, dbo, atol=2e-3, rtol=1e-3)
+
+
+def test_scale_dropout_and_mask_bits(be, ob):
+    x = g(5, 1000, seed=1)
+    for p, site in ((0.2, 1), (0.5, 77), (0.0, 3)):
+        yo = ob.scale_dropout(x, 1.5, (p, site))
+        yc = be.scale_dropout(x.cuda(), 1.5, (p, site))
+        assert torch.equal(yc.cpu() == 0, yo == 0)
+        close(yc, yo, atol=1e-6)
+
+
+def test_embedding(be, ob):
+    B, Ts, Tt, D, V = 3, 21, 6, 32, 11
+    sp, mf = g(B, Ts, 80, seed=1), g(80, seed=2)
+    masked = g(B, Ts, seed=3) > 0
+    close(be.mask_input_fwd(sp.cuda(), masked.cuda(), mf.cuda()), ob.mask_input_fwd(sp, masked, mf), atol=0, rtol=0)
+    close(be.mask_input_bwd(sp.cuda(), masked.cuda()), ob.mask_input_bwd(sp, masked), atol=1e-4)
+    sy, emb, seg = g(B, Ts, D, seed=4), g(V, D, seed=5), g(500, D, seed=6)
+    gen = torch.Generator().manual_seed(7)
+    text = torch.randint(0, V, (B, Tt), generator=gen)
+    text[0, 0] = V - 1  # padding row
+    sseg = torch.randint(0, 8, (B, Ts), generator=gen)
+    tseg = torch.randint(0, 8, (B, Tt), generator=gen)
+    sseg[0, 0] = 499
+    for dr in (None, (0.3, 5)):
+        dt = None if dr is None else (0.3, 6)
+        xo = ob.embed_assemble_fwd(sy, text, sseg, tseg, emb, seg, 3.0, drop_speech=dr, drop_text=dt)
+        xc = be.embed_assemble_fwd(sy.cuda(), text.cuda(), sseg.cuda(), tseg.cuda(), emb.cuda(), seg.cuda(), 3.0,
+                                   drop_speech=dr, drop_text=dt)
+        close(xc, xo, atol=1e-5)
+        dxs = g(B, Ts + Tt, D, seed=8)
+        o = ob.embed_assemble_bwd(dxs, text, sseg, tseg, V, 500, 3.0, V - 1, 499, drop_speech=dr, drop_text=dt)
+        c = be.embed_assemble_bwd(dxs.cuda(), text.cuda(), sseg.cuda(), tseg.cuda(), V, 500, 3.0, V - 1, 499,
+                                  drop_speech=dr, drop_text=dt)
+        for a, b in zip(c, o):
+            close(a, b, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,S,dk", [(2, 2, 19, 16), (1, 2, 130, 8), (2, 1, 64, 32)])
+def test_attention(be, ob, B, H, S, dk):
+    D = H * dk
+    qkv4, p = g(B, S, 4 * D, seed=1, scale=0.5), g(S, D, seed=2, scale=0.5)
+    keymask = torch.ones(B, S, dtype=torch.bool)
+    keymask[0, S - 3:] = False
+    aco, bdo = ob.attn_scores_fwd(qkv4, p, H)
+    acc, bdc = be.attn_scores_fwd(qkv4.cuda(), p.cuda(), H)
+    close(acc, aco)
+    close(bdc, bdo)
+    sc = 1.0 / math.sqrt(dk)
+    for dr in (None, (0.2, 4)):
+        Po, Pdo = ob.relpos_softmax_fwd(aco, bdo, keymask, sc, drop=dr)
+        Pc, Pdc = be.relpos_softmax_fwd(acc, bdc, keymask.cuda(), sc, drop=dr)
+        close(Pc, Po, atol=1e-5)
+        close(Pdc, Pdo, atol=1e-5)
+        assert float(Pc[0, :, :, S - 3:].abs().max()) == 0.0  # padded keys are exactly zero
+        cxo = ob.attn_pv_fwd(Pdo, qkv4, H)
+        cxc = be.attn_pv_fwd(Pdc, qkv4.cuda(), H)
+        close(cxc, cxo)
+        dctx = g(B, S, D, seed=5)
+        dq_o, dq_c = torch.zeros(B, S, 4 * D), torch.zeros(B, S, 4 * D, device="cuda")
+        dPo = ob.attn_pv_bwd(dctx, Pdo, qkv4, H, dq_o)
+        dPc = be.attn_pv_bwd(dctx.cuda(), Pdc, qkv4.cuda(), H, dq_c)
+        close(dPc, dPo)
+        dSo, dBo = ob.relpos_softmax_bwd(dPo, Po, sc, drop=dr)
+        dSc, dBc = be.relpos_softmax_bwd(dPc, Pc, sc, drop=dr)
+        close(dSc, dSo, atol=1e-5)
+        close(dBc, dBo, atol=1e-5)
+        dpo = ob.attn_scores_bwd(dSo, dBo, qkv4, p, H, dq_o)
+        dpc = be.attn_scores_bwd(dSc, dBc, qkv4.cuda(), p.cuda(), H, dq_c)
+        close(dpc, dpo)
+        close(dq_c, dq_o)
+
+
+def test_rel_shift_index_map_is_exact(be):
+    """BD' = rel_shift(BD) must be an exact gather (no arithmetic): feed integers, AC = 0, and
+    compare the pre-softmax ordering through a one-hot trick."""
+    S = 7
+    bd = torch.arange(S * S, dtype=torch.float32).view(1, 1, S, S)
+    want = O.rel_shift(bd)
+    # softmax of 50*onehot-ish: recover argmax per row instead -> use scale and compare P ordering
+    ac = torch.zeros(1, 1, S, S)
+    P, _ = be.relpos_softmax_fwd(ac.cuda(), bd.cuda(), torch.ones(1, S, dtype=torch.bool).cuda(), 1.0)
+    Pw = torch.softmax(want, -1)
+    close(P, Pw, atol=1e-6)
+
+
+@pytest.mark.parametrize("k,C,S", [(7, 96, 70), (31, 64, 130), (5, 16, 12)])
+def test_conv_module(be, ob, k, C, S):
+    B = 2
+    u, w, b = g(B, S, 2 * C, seed=1), g(C, k, seed=2, scale=0.3), g(C, seed=3)
+    zo = ob.glu_dwconv_fwd(u, w, b)
+    zc = be.glu_dwconv_fwd(u.cuda(), w.cuda(), b.cuda())
+    close(zc, zo)
+    dz = g(B, S, C, seed=4)
+    for a, bb in zip(be.glu_dwconv_bwd(dz.cuda(), u.cuda(), w.cuda()), ob.glu_dwconv_bwd(dz, u, w)):
+        close(a, bb, atol=5e-4, rtol=1e-3)
+    gam, bet = 1 + 0.2 * g(C, seed=5), 0.1 * g(C, seed=6)
+    for training in (True, False):
+        rm_o, rv_o, n_o = 0.1 * g(C, seed=7), 1 + 0.1 * g(C, seed=8).abs(), torch.tensor(3)
+        rm_c, rv_c, n_c = rm_o.clone().cuda(), rv_o.clone().cuda(), n_o.clone().cuda()
+        mo, ro = ob.bn_stats(zo, rm_o, rv_o, n_o, 0.1, 1e-5, training)
+        mc, rc = be.bn_stats(zc, rm_c, rv_c, n_c, 0.1, 1e-5, training)
+        close(mc, mo, atol=1e-5)
+        close(rc, ro, rtol=1e-4)
+        close(rm_c, rm_o, atol=1e-6)
+        close(rv_c, rv_o, atol=1e-5)
+        assert int(n_c) == int(n_o)
+        for act, dr, res in ((O.ACT_SWISH, None, None), (O.ACT_TANH, (0.5, 2), None), (O.ACT_NONE, (0.5, 3), zo)):
+            yo = ob.bn_act_fwd(zo, mo, ro, gam, bet, act, drop=dr, residual=res)
+            yc = be.bn_act_fwd(zc, mc, rc, gam.cuda(), bet.cuda(), act, drop=dr, residual=None if res is None else zc)
+            close(yc, yo, atol=1e-5)
+            dy = g(B, S, C, seed=9)
+            o = ob.bn_act_bwd(dy, zo, mo, ro, gam, bet, act, training, drop=dr, eps=1e-5)
+            c = be.bn_act_bwd(dy.cuda(), zc, mc, rc, gam.cuda(), bet.cuda(), act, training, drop=dr, eps=1e-5)
+            for a, bb in zip(c, o):
+                close(a, bb, atol=5e-4, rtol=1e-3)
+
+
+def test_masked_l1(be, ob):
+    B, T, C = 3, 50, 80
+    before, after, y = g(B, T, C, seed=1), g(B, T, C, seed=2), g(B, T, C, seed=3)
+    mask = g(B, T, seed=4) > 0.3
+    lo, do = ob.masked_l1_fwd(before, after, y, mask)
+    lc, dc = be.masked_l1_fwd(before.cuda(), after.cuda(), y.cuda(), mask.cuda())
+    close(lc, lo, atol=1e-4, rtol=1e-6)
+    close(dc, do, atol=0)
+    gl = torch.tensor([1.7])
+    for a, b in zip(be.masked_l1_bwd(gl.cuda(), before.cuda(), after.cuda(), y.cuda(), mask.cuda(), dc),
+                    ob.masked_l1_bwd(gl, before, after, y, mask, do)):
+        close(a, b, atol=1e-7)
+    # empty mask: loss 0, no NaN (den = 1e-10)
+    lc, dc = be.masked_l1_fwd(before.cuda(), after.cuda(), y.cuda(), torch.zeros(B, T, dtype=torch.bool).cuda())
+    assert float(lc) == 0.0
+
+
+def test_clip_adam_noam(be):
+    from a3t_b200 import _lib
+
+    n = 100_003
+    p, gr = g(n, seed=1), g(n, seed=2, scale=0.01)
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, gc, mc, vc = p.clone().cuda(), gr.clone().cuda(), m.clone().cuda(), v.clone().cuda()
+    sq = torch.zeros(1, dtype=torch.float64, device="cuda")
+    part = torch.zeros(1024, dtype=torch.float64, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for it in range(1, 4):
+        _lib.call("a3t_grad_sqnorm", gc.data_ptr(), n, sq.data_ptr(), part.data_ptr(), st)
+        _lib.call("a3t_adam_step", pc.data_ptr(), gc.data_ptr(), mc.data_ptr(), vc.data_ptr(), n, sq.data_ptr(),
+                  step.data_ptr(), 1.0, 384.0, 4000.0, 0.9, 0.999, 1e-8, 1.0, 1.0, None, st)
+        O.clip_adam_step(p, gr.clone(), m, v, it, O.noam_lr(1.0, 384, 4000, it))
+        assert int(step) == it
+        close(pc, p, atol=1e-6, rtol=1e-5)
+    # non-finite gradient: update skipped, step not advanced (trainer.py:640-656)
+    gc[5] = float("nan")
+    before = pc.clone()
+    _lib.call("a3t_grad_sqnorm", gc.data_ptr(), n, sq.data_ptr(), part.data_ptr(), st)
+    _lib.call("a3t_adam_step", pc.data_ptr(), gc.data_ptr(), mc.data_ptr(), vc.data_ptr(), n, sq.data_ptr(),
+              step.data_ptr(), 1.0, 384.0, 4000.0, 0.9, 0.999, 1e-8, 1.0, 1.0, None, st)
+    assert int(step) == 3 and torch.equal(pc, before)
