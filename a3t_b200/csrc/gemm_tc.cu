@@ -1,8 +1,637 @@
-// tcgen05 tensor-core GEMM (placeholder until the kernel lands: reports "unsupported").
+// tcgen05 tensor-core GEMM for sm_100a: the dense contractions of the A3T Conformer step.
+//
+//   * operands bf16, staged in shared memory by TMA (4-D tensor maps, 128-byte swizzle, zero OOB
+//     fill — the OOB fill is what implements the 1-D conv "same" padding and ragged edges),
+//   * fp32 accumulators in TMEM (2 x 256 columns, double buffered against the epilogue),
+//   * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, cta_group::1),
+//   * warp-specialised persistent CTAs (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
+//     TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/mask/dropout/residual -> global).
+//
+// Modes (include/a3t_b200.h): PLAIN (any of the four operand-major combinations, batched),
+// CONV (implicit 1-D conv: K loop over (tap, channel block), A rows shifted by tap - pad inside
+// their sequence) and WGRAD (reduction over rows of every sequence, both operands MN-major,
+// optional split-K with fp32 atomics).
+//
+// Replaces torch.nn.Linear / Conv1d / bmm calls of the reference: transformer/attention.py:55-96,
+// :185-202, transformer/multi_layer_conv.py:61-62, conformer/convolution.py:28-54,
+// tacotron2/decoder.py:189-238 and their autograd backward.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace a3t {
-int gemm_tc_launch(const A3tGemmDesc*, const void*, const void*, void*, const float*, const float*, const void*,
-                   const unsigned long long*, cudaStream_t, bool) {
-  return A3T_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
+constexpr int SMEM_BYTES_MAX = 227 * 1024;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int MAX_STAGES = 8;
+
+struct Params {
+  A3tGemmDesc d;
+  const float* bias;
+  const float* res;
+  const void* mask;
+  const unsigned long long* seed;
+  void* C;
+  uint32_t idesc;
+  int block_n;          // UMMA N (multiple of 16, <= 256)
+  int stages;
+  int a_mn, b_mn;       // 1 = operand is MN-major in global/shared memory
+  int m_tiles_per_seq;  // CONV: tiles per sequence, else all M tiles
+  int m_tiles;          // total M tiles (per batch entry)
+  int n_tiles_per_tap;  // WGRAD: N tiles per tap, else all N tiles
+  int n_tiles;          // total N tiles
+  int k_iters;          // total K iterations of one output tile
+  int splits;           // split-K factor (atomics when > 1)
+  int cblocks;          // CONV: ceil(cin / 64);  WGRAD: ceil(seq / 64)
+  int num_work;         // m_tiles * n_tiles * batch * splits
+  int a_c2, a_c3, b_c2, b_c3;  // 0 when that batch coordinate is pinned (stride 0 / size 1)
+  int vec_c, vec_r, vec_m;     // 16-byte vector access allowed for C / residual / mask
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0x3FF) == 0) {  // watchdog: a protocol bug must not hang the GPU
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
+//   K-major : 8-row groups 1024 B apart (SBO), LBO unused (=1)
+//   MN-major: 64-element MN atoms `lbo_bytes` apart, 8-k groups 1024 B apart (SBO)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  desc |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  desc |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  desc |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  desc |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return desc;
+}
+
+struct Work {
+  int z, b1, b2;
+  int seq_idx, m0;   // m0: row inside the sequence (CONV) or global row
+  int tap_n, n0;     // WGRAD: tap of the N tile and channel offset; else n0 = column offset
+  int k_begin, k_end;
+};
+
+__device__ __forceinline__ Work decode_work(const Params& p, int w) {
+  Work t;
+  int split = w % p.splits;
+  int r = w / p.splits;
+  int n_t = r % p.n_tiles;
+  r /= p.n_tiles;
+  int m_t = r % p.m_tiles;
+  t.z = r / p.m_tiles;
+  t.b1 = t.z / p.d.batch2;
+  t.b2 = t.z - t.b1 * p.d.batch2;
+  t.seq_idx = m_t / p.m_tiles_per_seq;
+  t.m0 = (m_t - t.seq_idx * p.m_tiles_per_seq) * BLOCK_M;
+  t.tap_n = n_t / p.n_tiles_per_tap;
+  t.n0 = (n_t - t.tap_n * p.n_tiles_per_tap) * p.block_n;
+  int per = (p.k_iters + p.splits - 1) / p.splits;
+  t.k_begin = split * per;
+  t.k_end = min(p.k_iters, t.k_begin + per);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers: 8 consecutive columns of one output row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue8(const Params& p, const Drop& dr, const uint32_t* acc, int m, int n8,
+                                          int nlim, int64_t crow, int64_t rrow, unsigned long long drow,
+                                          int tap_n) {
+  const A3tGemmDesc& d = p.d;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = d.alpha * __uint_as_float(acc[j]);
+  const bool full = n8 + 8 <= nlim;
+  const int ncol = (d.mode == A3T_GEMM_WGRAD) ? tap_n * d.cin + n8 : n8;  // logical column (bias / dropout index)
+  if (p.bias) {
+    if (full) {
+      float4 b0 = __ldg((const float4*)(p.bias + ncol)), b1 = __ldg((const float4*)(p.bias + ncol + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (n8 + j < nlim) v[j] += __ldg(p.bias + ncol + j);
+    }
+  }
+  if (d.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+  }
+  // element offset of column n8 inside C (and the mask, which shares C's strides)
+  const int64_t coff = (d.mode == A3T_GEMM_WGRAD) ? crow + (int64_t)tap_n * d.sc_tap + (int64_t)n8 * d.sc_n
+                                                  : crow + (int64_t)n8 * d.sc_n;
+  if (p.mask) {
+    if (full && p.vec_m) {
+      if (d.dtype_mask == A3T_BF16) {
+        uint4 mv = __ldg((const uint4*)((const __nv_bfloat16*)p.mask + coff));
+        const __nv_bfloat16* mb = (const __nv_bfloat16*)&mv;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (__bfloat162float(mb[j]) != 0.f) ? v[j] * d.mask_scale : 0.f;
+      } else {
+        float4 m0 = __ldg((const float4*)((const float*)p.mask + coff));
+        float4 m1 = __ldg((const float4*)((const float*)p.mask + coff + 4));
+        float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (mm[j] != 0.f) ? v[j] * d.mask_scale : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (n8 + j < nlim) {
+          float mv = load_as_f32(p.mask, d.dtype_mask, coff + (int64_t)j * d.sc_n);
+          v[j] = (mv != 0.f) ? v[j] * d.mask_scale : 0.f;
+        }
+    }
+  }
+  if (dr.on) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = drop_apply(dr, drow + (unsigned long long)(ncol + j), v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] *= d.out_scale;
+  if (p.res) {
+    const float* rp = p.res + rrow + (int64_t)n8 * d.sr_n;
+    if (full && p.vec_r) {
+      float4 r0 = __ldg((const float4*)rp), r1 = __ldg((const float4*)(rp + 4));
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (n8 + j < nlim) v[j] += __ldg(rp + (int64_t)j * d.sr_n);
+    }
+  }
+  if (p.splits > 1) {  // split-K partial sums (fp32 output, zero-initialised by the launcher)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (n8 + j < nlim) atomicAdd((float*)p.C + coff + (int64_t)j * d.sc_n, v[j]);
+    return;
+  }
+  if (full && p.vec_c) {
+    if (d.dtype_c == A3T_BF16) {
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *(uint4*)((__nv_bfloat16*)p.C + coff) = *(const uint4*)h;
+    } else {
+      float* cp = (float*)p.C + coff;
+      *(float4*)cp = make_float4(v[0], v[1], v[2], v[3]);
+      *(float4*)(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (n8 + j < nlim) store_from_f32(p.C, d.dtype_c, coff + (int64_t)j * d.sc_n, v[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // 8-byte mbarriers after the tiles
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const A3tGemmDesc& d = p.d;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int a_boxes = p.a_mn ? BLOCK_M / 64 : 1;
+      const int b_boxes = p.b_mn ? p.block_n / 64 : 1;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const Work t = decode_work(p, w);
+        for (int kit = t.k_begin; kit < t.k_end; kit++) {
+          int ai, ao, a2, a3, bi, bo, b2, b3;  // (inner, outer, dim2, dim3) coordinates
+          if (d.mode == A3T_GEMM_CONV) {
+            int tap = kit / p.cblocks, c0 = (kit - tap * p.cblocks) * BLOCK_K;
+            ai = c0; ao = t.m0 + tap - d.pad; a2 = t.seq_idx; a3 = 0;
+            bi = tap * d.cin + c0; bo = t.n0; b2 = 0; b3 = 0;
+          } else if (d.mode == A3T_GEMM_WGRAD) {
+            int sq = kit / p.cblocks, s0 = (kit - sq * p.cblocks) * BLOCK_K;
+            ai = t.m0; ao = s0; a2 = sq; a3 = 0;
+            bi = t.n0; bo = s0 + t.tap_n - d.pad; b2 = sq; b3 = 0;
+          } else {
+            int k0 = kit * BLOCK_K;
+            if (p.a_mn) { ai = t.m0; ao = k0; } else { ai = k0; ao = t.m0; }
+            if (p.b_mn) { bi = t.n0; bo = k0; } else { bi = k0; bo = t.n0; }
+            a2 = t.b2 * p.a_c2; a3 = t.b1 * p.a_c3;
+            b2 = t.b2 * p.b_c2; b3 = t.b1 * p.b_c3;
+          }
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + A_STAGE_BYTES;
+          for (int j = 0; j < a_boxes; j++)
+            tma_load_4d(sa + j * (BLOCK_K * 128), &tmA, full_bar(s), ai + 64 * j, ao, a2, a3);
+          for (int j = 0; j < b_boxes; j++)
+            tma_load_4d(sb + j * (BLOCK_K * 128), &tmB, full_bar(s), bi + 64 * j, bo, b2, b3);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      // per-instruction K advance inside a stage: K-major = 32 B along the swizzled row,
+      // MN-major = 16 k-rows of 128 B
+      const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t a_lbo = p.a_mn ? BLOCK_K * 128 : 16;
+      const uint32_t b_lbo = p.b_mn ? BLOCK_K * 128 : 16;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const Work t = decode_work(p, w);
+        mbar_wait(tempty_bar(as), aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+        for (int kit = t.k_begin; kit < t.k_end; kit++) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo);
+            uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo);
+            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kit > t.k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage once the MMAs above have read it
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;       // row of the tile owned by this thread
+    int as = 0;
+    uint32_t aph = 0;
+    const Drop dr = make_drop(d.drop_p, p.seed, d.drop_site);
+    const int nchunks = (p.block_n + 31) / 32;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+      const Work t = decode_work(p, w);
+      int m;
+      bool row_ok;
+      if (d.mode == A3T_GEMM_CONV) {
+        row_ok = (t.m0 + row) < d.seq;
+        m = t.seq_idx * d.seq + t.m0 + row;
+      } else {
+        m = t.m0 + row;
+        row_ok = m < d.M;
+      }
+      const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
+      const int64_t crow = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)m * d.sc_m;
+      const int64_t rrow = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)m * d.sr_m;
+      const unsigned long long drow = ((unsigned long long)t.z * d.M + m) * (unsigned long long)d.N;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < nchunks; c++) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; g8++) {
+            int n8 = t.n0 + c * 32 + g8 * 8;
+            if (n8 < nlim && c * 32 + g8 * 8 < p.block_n) epilogue8(p, dr, acc + g8 * 8, m, n8, nlim, crow, rrow, drow, t.tap_n);
+          }
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map: dims[0] contiguous; strides in elements for dims 1..3
+static bool encode_map(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3],
+                       const int box[4]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; i++) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+  }
+  for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides[i] * 2;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static inline bool mul8(int64_t v) { return (v & 7) == 0; }
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace tc
+
+int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C, const float* bias,
+                   const float* res, const void* mask, const unsigned long long* seed, cudaStream_t st,
+                   bool probe_only) {
+  using namespace tc;
+  const A3tGemmDesc& d = *dp;
+  // ---- qualification ------------------------------------------------------------------------
+  if (d.dtype_a != A3T_BF16 || d.dtype_b != A3T_BF16) return A3T_ERR_UNSUPPORTED;
+  if (d.M < 1 || d.N < 1 || d.K < 1) return A3T_ERR_UNSUPPORTED;
+  if (!al16(A) || !al16(B)) return A3T_ERR_UNSUPPORTED;
+  const int nbatch = d.batch1 * d.batch2;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.d = d;
+  int64_t adims[4], astr[3], bdims[4], bstr[3];
+  int abox[4] = {64, 1, 1, 1}, bbox[4] = {64, 1, 1, 1};
+  p.a_c2 = p.a_c3 = p.b_c2 = p.b_c3 = 0;
+  int nlim = d.N;  // extent one "N tile row" covers
+  if (d.mode == A3T_GEMM_CONV) {
+    if (nbatch != 1 || d.sa_k != 1 || d.sb_k != 1 || d.sb_tap != d.cin || !mul8(d.sa_m) || !mul8(d.sb_n))
+      return A3T_ERR_UNSUPPORTED;
+    p.a_mn = p.b_mn = 0;
+    adims[0] = d.cin; adims[1] = d.seq; adims[2] = d.M / d.seq; adims[3] = 1;
+    astr[0] = d.sa_m; astr[1] = (int64_t)d.seq * d.sa_m; astr[2] = astr[1];
+    bdims[0] = d.K; bdims[1] = d.N; bdims[2] = 1; bdims[3] = 1;
+    bstr[0] = d.sb_n; bstr[1] = d.sb_n; bstr[2] = d.sb_n;
+    p.m_tiles_per_seq = ceil_div(d.seq, BLOCK_M);
+    p.m_tiles = p.m_tiles_per_seq * (d.M / d.seq);
+    p.cblocks = ceil_div(d.cin, BLOCK_K);
+    p.k_iters = d.taps * p.cblocks;
+  } else if (d.mode == A3T_GEMM_WGRAD) {
+    if (nbatch != 1 || d.sa_m != 1 || d.sb_n != 1 || !mul8(d.sa_k) || !mul8(d.sb_k)) return A3T_ERR_UNSUPPORTED;
+    p.a_mn = p.b_mn = 1;
+    adims[0] = d.M; adims[1] = d.seq; adims[2] = d.K / d.seq; adims[3] = 1;
+    astr[0] = d.sa_k; astr[1] = (int64_t)d.seq * d.sa_k; astr[2] = astr[1];
+    bdims[0] = d.cin; bdims[1] = d.seq; bdims[2] = d.K / d.seq; bdims[3] = 1;
+    bstr[0] = d.sb_k; bstr[1] = (int64_t)d.seq * d.sb_k; bstr[2] = bstr[1];
+    p.m_tiles_per_seq = p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.cblocks = ceil_div(d.seq, BLOCK_K);
+    p.k_iters = (d.K / d.seq) * p.cblocks;
+    nlim = d.cin;
+  } else {
+    if (d.sa_k == 1 && mul8(d.sa_m)) p.a_mn = 0;
+    else if (d.sa_m == 1 && mul8(d.sa_k)) p.a_mn = 1;
+    else return A3T_ERR_UNSUPPORTED;
+    if (d.sb_k == 1 && mul8(d.sb_n)) p.b_mn = 0;
+    else if (d.sb_n == 1 && mul8(d.sb_k)) p.b_mn = 1;
+    else return A3T_ERR_UNSUPPORTED;
+    if (!mul8(d.sa_b1) || !mul8(d.sa_b2) || !mul8(d.sb_b1) || !mul8(d.sb_b2)) return A3T_ERR_UNSUPPORTED;
+    const int64_t a_row = p.a_mn ? d.sa_k : d.sa_m, b_row = p.b_mn ? d.sb_k : d.sb_n;
+    adims[0] = p.a_mn ? d.M : d.K; adims[1] = p.a_mn ? d.K : d.M;
+    bdims[0] = p.b_mn ? d.N : d.K; bdims[1] = p.b_mn ? d.K : d.N;
+    astr[0] = a_row; bstr[0] = b_row;
+    p.a_c2 = (d.batch2 > 1 && d.sa_b2 != 0); p.a_c3 = (d.batch1 > 1 && d.sa_b1 != 0);
+    p.b_c2 = (d.batch2 > 1 && d.sb_b2 != 0); p.b_c3 = (d.batch1 > 1 && d.sb_b1 != 0);
+    adims[2] = p.a_c2 ? d.batch2 : 1; astr[1] = p.a_c2 ? d.sa_b2 : a_row;
+    adims[3] = p.a_c3 ? d.batch1 : 1; astr[2] = p.a_c3 ? d.sa_b1 : a_row;
+    bdims[2] = p.b_c2 ? d.batch2 : 1; bstr[1] = p.b_c2 ? d.sb_b2 : b_row;
+    bdims[3] = p.b_c3 ? d.batch1 : 1; bstr[2] = p.b_c3 ? d.sb_b1 : b_row;
+    p.m_tiles_per_seq = p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.k_iters = ceil_div(d.K, BLOCK_K);
+  }
+  for (int i = 0; i < 3; i++)
+    if (astr[i] <= 0 || bstr[i] <= 0 || astr[i] >= ((int64_t)1 << 38) || bstr[i] >= ((int64_t)1 << 38))
+      return A3T_ERR_UNSUPPORTED;
+  if (d.dtype_c != A3T_F32 && d.dtype_c != A3T_BF16) return A3T_ERR_UNSUPPORTED;
+  if (mask && d.dtype_mask != A3T_F32 && d.dtype_mask != A3T_BF16) return A3T_ERR_UNSUPPORTED;
+  if (probe_only) return get_encode() ? A3T_OK : A3T_ERR_UNSUPPORTED;
+
+  // ---- tile shape: minimise (waves x tile width) over the legal UMMA N values -------------------
+  const int sms = num_sms();
+  int best_bn = 0;
+  double best_cost = 1e30;
+  const int cands[5] = {256, 192, 128, 64, ((nlim + 15) / 16) * 16};
+  for (int ci = 0; ci < 5; ci++) {
+    int bn = cands[ci];
+    if (bn > 256 || bn < 16) continue;
+    if (p.b_mn && (bn % 64)) continue;
+    int nt = ceil_div(nlim, bn) * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
+    int64_t tiles = (int64_t)p.m_tiles * nt * nbatch;
+    int64_t waves = (tiles + sms - 1) / sms;
+    double cost = (double)waves * (bn + 24);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+  }
+  if (best_bn == 0) return A3T_ERR_UNSUPPORTED;
+  p.block_n = best_bn;
+  p.n_tiles_per_tap = ceil_div(nlim, p.block_n);
+  p.n_tiles = p.n_tiles_per_tap * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
+  int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * nbatch;
+  if (tiles > (1 << 30)) return A3T_ERR_UNSUPPORTED;
+
+  // ---- split-K: only where the output is a small dense fp32 matrix with a plain epilogue ---------
+  p.splits = 1;
+  if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && !bias && !res && !mask && d.drop_p == 0.f && !d.relu &&
+      d.sc_tap == 1 && d.sc_n == d.taps && d.sc_m == (int64_t)d.taps * d.cin && tiles < sms) {
+    int s = (int)(sms / tiles);
+    int maxs = p.k_iters / 8;
+    if (s > maxs) s = maxs;
+    if (s > 1) {
+      int per = (p.k_iters + s - 1) / s;
+      s = (p.k_iters + per - 1) / per;  // no empty split
+      p.splits = s;
+    }
+  }
+  p.num_work = (int)tiles * p.splits;
+
+  abox[1] = p.a_mn ? BLOCK_K : BLOCK_M;
+  bbox[1] = p.b_mn ? BLOCK_K : p.block_n;
+  const uint32_t stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  const int bar_bytes = 8 * (2 * MAX_STAGES + 4) + 16;
+  p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes) / (int)stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.stages < 2) return A3T_ERR_UNSUPPORTED;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + bar_bytes;
+
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  p.bias = bias; p.res = res; p.mask = mask; p.seed = seed; p.C = C;
+  const int esc = d.dtype_c == A3T_BF16 ? 8 : 4;  // elements per 16 bytes
+  p.vec_c = (d.mode != A3T_GEMM_WGRAD) && d.sc_n == 1 && al16(C) && (d.sc_m % esc) == 0 && (d.sc_b1 % esc) == 0 &&
+            (d.sc_b2 % esc) == 0;
+  p.vec_r = res && d.sr_n == 1 && al16(res) && (d.sr_m % 4) == 0 && (d.sr_b1 % 4) == 0 && (d.sr_b2 % 4) == 0;
+  const int esm = d.dtype_mask == A3T_BF16 ? 8 : 4;
+  p.vec_m = mask && (d.mode != A3T_GEMM_WGRAD) && d.sc_n == 1 && al16(mask) && (d.sc_m % esm) == 0 &&
+            (d.sc_b1 % esm) == 0 && (d.sc_b2 % esm) == 0;
+  if (bias && ((uintptr_t)bias & 15)) return A3T_ERR_UNSUPPORTED;
+
+  CUtensorMap tmA, tmB;
+  if (!encode_map(&tmA, A, adims, astr, abox) || !encode_map(&tmB, B, bdims, bstr, bbox)) return A3T_ERR_UNSUPPORTED;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return A3T_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (p.splits > 1) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)d.M * d.sc_m * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: memset: %s", cudaGetErrorString(e));
+      return A3T_ERR_CUDA;
+    }
+  }
+  int grid = p.num_work < sms ? p.num_work : sms;
+  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
+  return check_launch("gemm_tc");
 }
 }  // namespace a3t

@@ -66,10 +66,10 @@ class DataParallelTrainer:
         gloss = torch.full((1,), float(B), dtype=torch.float32, device=self.device)
         G = graph.backward(ops, P, wc, cfg, ctx, gloss)
         torch._foreach_copy_([self.gviews[n] for n in self.names], [G[n].view(self.gviews[n].shape) for n in self.names])
-        self.stats[0:1] = loss * float(B)
-        self.stats[1:2] = loss * float(B)
-        self.stats[2] = float(B)
-        self.stats[3] = 0.0
+        self.stats[0:1].copy_(loss).mul_(float(B))
+        self.stats[1:2].copy_(loss).mul_(float(B))
+        self.stats[2:3].fill_(float(B))
+        self.stats[3:4].fill_(0.0)
         if self.world > 1:  # C3 (+C5/C6 piggy-backed): the single collective of the step
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -81,13 +81,16 @@ def test_bf16_mode_is_close(fx):
     rel = abs(float(loss) - float(fx["loss_train"])) / abs(float(fx["loss_train"]))
     assert rel < 2e-2, rel
     loss.backward()
-    cos = []
+    cos = {}
     for n, p in m.named_parameters():
         gref = fx["grads"][n].flatten()
-        if float(gref.abs().max()) < 1e-6:
+        # linear_k.bias (softmax shift invariance) and depthwise_conv.bias (followed by BatchNorm) have a
+        # mathematically zero gradient: only rounding noise to compare
+        if n.endswith("linear_k.bias") or n.endswith("depthwise_conv.bias") or float(gref.abs().max()) < 1e-5:
             continue
-        cos.append(float(torch.nn.functional.cosine_similarity(p.grad.flatten().cpu(), gref, dim=0)))
-    assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.99, (min(cos), sum(cos) / len(cos))
+        cos[n] = float(torch.nn.functional.cosine_similarity(p.grad.flatten().cpu(), gref, dim=0))
+    worst = min(cos, key=cos.get)
+    assert cos[worst] > 0.9 and sum(cos.values()) / len(cos) > 0.99, (worst, cos[worst], sum(cos.values()) / len(cos))
 
 
 def test_dropout_training_runs_and_is_reproducible(fx):
