@@ -39,10 +39,8 @@ __device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, fl
 }
 
 // ---- stateless dropout mask (bit-identical twin: oracle/a3t_oracle.py::keep_mask) -----------
-__device__ __host__ __forceinline__ uint32_t fmix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-  return x;
-}
+// keep(idx) = top 24 bits of a 3-multiply integer hash of (idx, seed, site) >= p * 2^24.  Eight integer
+// instructions per element: the mask is regenerated in every epilogue/backward instead of stored.
 struct Drop {
   uint32_t thr;      // keep iff (hash>>8) >= thr ; thr = (uint32)(p * 2^24)
   float inv_keep;    // 1/(1-p)
@@ -62,13 +60,18 @@ __device__ __forceinline__ Drop make_drop(float p, const unsigned long long* see
   }
   return d;
 }
-__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
-  uint32_t x = (uint32_t)(idx & 0xFFFFFFFFull) ^ ((uint32_t)(idx >> 32) * 0x85EBCA6Bu);
-  x ^= d.k0;
-  x = fmix32(x);
-  x += d.k1;
-  x = fmix32(x);
+// fold a 64-bit element index to the 32-bit hash input (identity for tensors below 2^32 elements)
+__device__ __host__ __forceinline__ uint32_t drop_fold(unsigned long long idx) {
+  return (uint32_t)(idx & 0xFFFFFFFFull) ^ ((uint32_t)(idx >> 32) * 0x85EBCA6Bu);
+}
+__device__ __forceinline__ bool drop_keep32(const Drop& d, uint32_t folded) {
+  uint32_t x = (folded ^ d.k0) * 0x9E3779B1u + d.k1;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= x >> 15; x *= 0x846CA68Bu;
   return (x >> 8) >= d.thr;
+}
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  return drop_keep32(d, drop_fold(idx));
 }
 __device__ __forceinline__ float drop_apply(const Drop& d, unsigned long long idx, float v) {
   if (!d.on) return v;

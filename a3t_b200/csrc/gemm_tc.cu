@@ -5,7 +5,8 @@
 //   * fp32 accumulators in TMEM (2 x 256 columns, double buffered against the epilogue),
 //   * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, cta_group::1),
 //   * warp-specialised persistent CTAs (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
-//     TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/mask/dropout/residual -> global).
+//     TMEM owner, warps 2..9 = epilogue (tcgen05.ld -> smem transpose -> bias/ReLU/mask/dropout/
+//     residual -> coalesced global stores).
 //
 // Modes (include/a3t_b200.h): PLAIN (any of the four operand-major combinations, batched),
 // CONV (implicit 1-D conv: K loop over (tap, channel block), A rows shifted by tap - pad inside
@@ -16,6 +17,7 @@
 // :185-202, transformer/multi_layer_conv.py:61-62, conformer/convolution.py:28-54,
 // tacotron2/decoder.py:189-238 and their autograd backward.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,7 +27,9 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 transposition buffer per epilogue warp
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
 constexpr int SMEM_BYTES_MAX = 227 * 1024;
@@ -166,103 +170,107 @@ __device__ __forceinline__ Work decode_work(const Params& p, int w) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue helpers: 8 consecutive columns of one output row
+// epilogue helper: 4 consecutive columns of one output row (lane layout after the smem transpose:
+// 8 lanes cover 32 consecutive columns of a row, a warp instruction touches 4 rows x 128 B)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue8(const Params& p, const Drop& dr, const uint32_t* acc, int m, int n8,
-                                          int nlim, int64_t crow, int64_t rrow, unsigned long long drow,
-                                          int tap_n) {
+__device__ __forceinline__ void epilogue4(const Params& p, const Drop& dr, float4 a, int n4, int nlim, int64_t crow,
+                                          int64_t rrow, unsigned long long drow, int tap_n) {
   const A3tGemmDesc& d = p.d;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) v[j] = d.alpha * __uint_as_float(acc[j]);
-  const bool full = n8 + 8 <= nlim;
-  const int ncol = (d.mode == A3T_GEMM_WGRAD) ? tap_n * d.cin + n8 : n8;  // logical column (bias / dropout index)
+  float v[4] = {d.alpha * a.x, d.alpha * a.y, d.alpha * a.z, d.alpha * a.w};
+  const bool full = n4 + 4 <= nlim;
+  const int ncol = (d.mode == A3T_GEMM_WGRAD) ? tap_n * d.cin + n4 : n4;  // logical column (bias / dropout index)
   if (p.bias) {
     if (full) {
-      float4 b0 = __ldg((const float4*)(p.bias + ncol)), b1 = __ldg((const float4*)(p.bias + ncol + 4));
+      float4 b0 = __ldg((const float4*)(p.bias + ncol));
       v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (n8 + j < nlim) v[j] += __ldg(p.bias + ncol + j);
+      for (int j = 0; j < 4; j++)
+        if (n4 + j < nlim) v[j] += __ldg(p.bias + ncol + j);
     }
   }
   if (d.relu) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
   }
-  // element offset of column n8 inside C (and the mask, which shares C's strides)
-  const int64_t coff = (d.mode == A3T_GEMM_WGRAD) ? crow + (int64_t)tap_n * d.sc_tap + (int64_t)n8 * d.sc_n
-                                                  : crow + (int64_t)n8 * d.sc_n;
+  // element offset of column n4 inside C (and the mask, which shares C's strides)
+  const int64_t coff = (d.mode == A3T_GEMM_WGRAD) ? crow + (int64_t)tap_n * d.sc_tap + (int64_t)n4 * d.sc_n
+                                                  : crow + (int64_t)n4 * d.sc_n;
   if (p.mask) {
     if (full && p.vec_m) {
+      float mm[4];
       if (d.dtype_mask == A3T_BF16) {
-        uint4 mv = __ldg((const uint4*)((const __nv_bfloat16*)p.mask + coff));
+        uint2 mv = __ldg((const uint2*)((const __nv_bfloat16*)p.mask + coff));
         const __nv_bfloat16* mb = (const __nv_bfloat16*)&mv;
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = (__bfloat162float(mb[j]) != 0.f) ? v[j] * d.mask_scale : 0.f;
+        for (int j = 0; j < 4; j++) mm[j] = __bfloat162float(mb[j]);
       } else {
         float4 m0 = __ldg((const float4*)((const float*)p.mask + coff));
-        float4 m1 = __ldg((const float4*)((const float*)p.mask + coff + 4));
-        float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = (mm[j] != 0.f) ? v[j] * d.mask_scale : 0.f;
+        mm[0] = m0.x; mm[1] = m0.y; mm[2] = m0.z; mm[3] = m0.w;
       }
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = (mm[j] != 0.f) ? v[j] * d.mask_scale : 0.f;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (n8 + j < nlim) {
+      for (int j = 0; j < 4; j++)
+        if (n4 + j < nlim) {
           float mv = load_as_f32(p.mask, d.dtype_mask, coff + (int64_t)j * d.sc_n);
           v[j] = (mv != 0.f) ? v[j] * d.mask_scale : 0.f;
         }
     }
   }
   if (dr.on) {
+    const unsigned long long idx0 = drow + (unsigned long long)ncol;
+    const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+    if (lo <= 0xFFFFFFF0u) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = drop_apply(dr, drow + (unsigned long long)(ncol + j), v[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) v[j] *= d.out_scale;
-  if (p.res) {
-    const float* rp = p.res + rrow + (int64_t)n8 * d.sr_n;
-    if (full && p.vec_r) {
-      float4 r0 = __ldg((const float4*)rp), r1 = __ldg((const float4*)(rp + 4));
-      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * dr.inv_keep : 0.f;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (n8 + j < nlim) v[j] += __ldg(rp + (int64_t)j * d.sr_n);
+      for (int j = 0; j < 4; j++) v[j] = drop_keep(dr, idx0 + j) ? v[j] * dr.inv_keep : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[j] *= d.out_scale;
+  if (p.res) {
+    const float* rp = p.res + rrow + (int64_t)n4 * d.sr_n;
+    if (full && p.vec_r) {
+      float4 r0 = __ldg((const float4*)rp);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (n4 + j < nlim) v[j] += __ldg(rp + (int64_t)j * d.sr_n);
     }
   }
   if (p.splits > 1) {  // split-K partial sums (fp32 output, zero-initialised by the launcher)
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (n8 + j < nlim) atomicAdd((float*)p.C + coff + (int64_t)j * d.sc_n, v[j]);
+    for (int j = 0; j < 4; j++)
+      if (n4 + j < nlim) atomicAdd((float*)p.C + coff + (int64_t)j * d.sc_n, v[j]);
     return;
   }
   if (full && p.vec_c) {
     if (d.dtype_c == A3T_BF16) {
-      __nv_bfloat162 h[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      *(uint4*)((__nv_bfloat16*)p.C + coff) = *(const uint4*)h;
+      __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v[0], v[1]), __floats2bfloat162_rn(v[2], v[3])};
+      *(uint2*)((__nv_bfloat16*)p.C + coff) = *(const uint2*)h;
     } else {
-      float* cp = (float*)p.C + coff;
-      *(float4*)cp = make_float4(v[0], v[1], v[2], v[3]);
-      *(float4*)(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      *(float4*)((float*)p.C + coff) = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (n8 + j < nlim) store_from_f32(p.C, d.dtype_c, coff + (int64_t)j * d.sc_n, v[j]);
+    for (int j = 0; j < 4; j++)
+      if (n4 + j < nlim) store_from_f32(p.C, d.dtype_c, coff + (int64_t)j * d.sc_n, v[j]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// EPI: -1 = generic epilogue (any strides, WGRAD scatter, split-K atomics); otherwise a bit set
+// EPI_MASK | EPI_DROP | EPI_RES | EPI_BF16 selecting the specialised vectorised epilogue.
+constexpr int EPI_MASK = 1, EPI_DROP = 2, EPI_RES = 4, EPI_BF16 = 8;
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ Params p) {
@@ -272,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
   const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // 8-byte mbarriers after the tiles
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;   // per-warp transposition buffers
+  const uint32_t bar_base = epi_base + NUM_EPI_WARPS * EPI_STAGE_BYTES;  // 8-byte mbarriers after them
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
@@ -288,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -377,46 +386,190 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================================== epilogue =========================================
-    const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;       // row of the tile owned by this thread
+    // 8 warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-2)/4 the odd/even 32-column
+    // chunks.  Each chunk: tcgen05.ld (thread = row) -> swizzled smem transpose -> lanes along the
+    // row, so residual/mask loads and the C stores are coalesced 128-byte row segments.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t stg = epi_base + ew * EPI_STAGE_BYTES;
     int as = 0;
     uint32_t aph = 0;
     const Drop dr = make_drop(d.drop_p, p.seed, d.drop_site);
     const int nchunks = (p.block_n + 31) / 32;
-    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
-      const Work t = decode_work(p, w);
-      int m;
-      bool row_ok;
-      if (d.mode == A3T_GEMM_CONV) {
-        row_ok = (t.m0 + row) < d.seq;
-        m = t.seq_idx * d.seq + t.m0 + row;
-      } else {
-        m = t.m0 + row;
-        row_ok = m < d.M;
-      }
-      const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
-      const int64_t crow = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)m * d.sc_m;
-      const int64_t rrow = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)m * d.sr_m;
-      const unsigned long long drow = ((unsigned long long)t.z * d.M + m) * (unsigned long long)d.N;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < nchunks; c++) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+    const int rsub = lane >> 3, c4 = lane & 7;
+    const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
+    if constexpr (EPI >= 0) {
+      // ---- specialised path: PLAIN/CONV, unit column stride, N % 4 == 0, 16-byte aligned rows ----
+      constexpr bool kMask = EPI & EPI_MASK, kDrop = EPI & EPI_DROP, kRes = EPI & EPI_RES, kBf16 = EPI & EPI_BF16;
+      const float alpha = d.alpha, out_scale = d.out_scale, mask_scale = d.mask_scale;
+      const bool relu = d.relu != 0;
+      const float drop_mul = kDrop ? dr.inv_keep * out_scale : out_scale;
+      const int row_lim = (d.mode == A3T_GEMM_CONV) ? d.seq : d.M;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const Work t = decode_work(p, w);
+        const int row0 = t.m0 + q * 32 + rsub;                       // row inside the sequence / matrix
+        const int mrow0 = (d.mode == A3T_GEMM_CONV) ? t.seq_idx * d.seq + row0 : row0;  // row inside C
+        const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)mrow0 * d.sc_m;
+        const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)mrow0 * d.sr_m;
+        const unsigned long long dbase = ((unsigned long long)t.z * d.M + mrow0) * (unsigned long long)d.N;
+        bool waited = false, released = false;
+        for (int c = half; c < nchunks; c += 2) {
+          const int col = c * 32 + c4 * 4;
+          const int n4 = t.n0 + col;
+          const bool col_ok = col < p.block_n && n4 < d.N;
+          // operands of the epilogue that live in global memory: issue the loads before waiting on TMEM
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && col_ok) bias4 = __ldg((const float4*)(p.bias + n4));
+          float4 rv[8];
+          uint2 mk[8];
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const bool ok = col_ok && (row0 + it * 4) < row_lim;
+            if constexpr (kRes) {
+              rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) rv[it] = __ldg((const float4*)(p.res + rbase + (int64_t)it * 4 * d.sr_m + n4));
+            }
+            if constexpr (kMask) {
+              mk[it] = make_uint2(0u, 0u);
+              if (ok) mk[it] = __ldg((const uint2*)((const __nv_bfloat16*)p.mask + cbase + (int64_t)it * 4 * d.sc_m + n4));
+            }
+          }
+          if (!waited) {
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + c * 32, acc);
+          tmem_ld_wait();
+          if (c + 2 >= nchunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            released = true;
+          }
+#pragma unroll
+          for (int g4 = 0; g4 < 8; g4++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((g4 ^ (lane & 7)) << 4)),
+                         "r"(acc[4 * g4]), "r"(acc[4 * g4 + 1]), "r"(acc[4 * g4 + 2]), "r"(acc[4 * g4 + 3])
+                         : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const int R = it * 4 + rsub;
+            float4 a;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                         : "r"(stg + R * 128 + ((c4 ^ (R & 7)) << 4))
+                         : "memory");
+            float v[4] = {fmaf(alpha, a.x, bias4.x), fmaf(alpha, a.y, bias4.y), fmaf(alpha, a.z, bias4.z),
+                          fmaf(alpha, a.w, bias4.w)};
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+            if constexpr (kMask) {
+              const __nv_bfloat16* mb = (const __nv_bfloat16*)&mk[it];
+#pragma unroll
+              for (int j = 0; j < 4; j++) v[j] = (__bfloat162float(mb[j]) != 0.f) ? v[j] * mask_scale : 0.f;
+            }
+            if constexpr (kDrop) {
+              const unsigned long long idx0 = dbase + (unsigned long long)it * 4ull * (unsigned long long)d.N + n4;
+              const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+              if (lo <= 0xFFFFFFF0u) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * drop_mul : 0.f;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = drop_keep(dr, idx0 + j) ? v[j] * drop_mul : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; j++) v[j] *= out_scale;
+            }
+            if constexpr (kRes) {
+              v[0] += rv[it].x; v[1] += rv[it].y; v[2] += rv[it].z; v[3] += rv[it].w;
+            }
+            if (col_ok && (row0 + it * 4) < row_lim) {
+              const int64_t coff = cbase + (int64_t)it * 4 * d.sc_m + n4;
+              if constexpr (kBf16) {
+                __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v[0], v[1]), __floats2bfloat162_rn(v[2], v[3])};
+                *(uint2*)((__nv_bfloat16*)p.C + coff) = *(const uint2*)h;
+              } else {
+                *(float4*)((float*)p.C + coff) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (!waited) {
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+        }
+        if (!released) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        if (row_ok) {
-#pragma unroll
-          for (int g8 = 0; g8 < 4; g8++) {
-            int n8 = t.n0 + c * 32 + g8 * 8;
-            if (n8 < nlim && c * 32 + g8 * 8 < p.block_n) epilogue8(p, dr, acc + g8 * 8, m, n8, nlim, crow, rrow, drow, t.tap_n);
-          }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    } else
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+      const Work t = decode_work(p, w);
+      const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2;
+      const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      bool released = false;
+      for (int c = half; c < nchunks; c += 2) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        if (c + 2 >= nchunks) {  // this warp has read all its columns: hand the TMEM stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+          released = true;
         }
+#pragma unroll
+        for (int g4 = 0; g4 < 8; g4++)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((g4 ^ (lane & 7)) << 4)),
+                       "r"(acc[4 * g4]), "r"(acc[4 * g4 + 1]), "r"(acc[4 * g4 + 2]), "r"(acc[4 * g4 + 3])
+                       : "memory");
+        __syncwarp();
+        const int col = c * 32 + c4 * 4;       // column inside the tile
+        const int n4 = t.n0 + col;             // column inside C (channel inside the tap for WGRAD)
+        const bool col_ok = col < p.block_n && n4 < nlim;
+#pragma unroll 2
+        for (int it = 0; it < 8; it++) {
+          const int R = it * 4 + rsub;
+          float4 a;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(stg + R * 128 + ((c4 ^ (R & 7)) << 4))
+                       : "memory");
+          const int row = t.m0 + q * 32 + R;
+          int m;
+          bool row_ok;
+          if (d.mode == A3T_GEMM_CONV) {
+            row_ok = row < d.seq;
+            m = t.seq_idx * d.seq + row;
+          } else {
+            m = row;
+            row_ok = m < d.M;
+          }
+          if (row_ok && col_ok)
+            epilogue4(p, dr, a, n4, nlim, cbase + (int64_t)m * d.sc_m, rbase + (int64_t)m * d.sr_m,
+                      ((unsigned long long)t.z * d.M + m) * (unsigned long long)d.N, t.tap_n);
+        }
+        __syncwarp();
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -569,6 +722,10 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
   }
   if (best_bn == 0) return A3T_ERR_UNSUPPORTED;
+  if (const char* e = getenv("A3T_TC_BN")) {  // tuning experiments only
+    int v = atoi(e);
+    if (v >= 16 && v <= 256 && v % 16 == 0 && !(p.b_mn && v % 64)) best_bn = v;
+  }
   p.block_n = best_bn;
   p.n_tiles_per_tap = ceil_div(nlim, p.block_n);
   p.n_tiles = p.n_tiles_per_tap * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
@@ -594,10 +751,15 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   bbox[1] = p.b_mn ? BLOCK_K : p.block_n;
   const uint32_t stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
   const int bar_bytes = 8 * (2 * MAX_STAGES + 4) + 16;
-  p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes) / (int)stage_bytes;
+  const int epi_bytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes - epi_bytes) / (int)stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (const char* e = getenv("A3T_TC_STAGES")) {
+    int v = atoi(e);
+    if (v >= 2 && v < p.stages) p.stages = v;
+  }
   if (p.stages < 2) return A3T_ERR_UNSUPPORTED;
-  const int smem_bytes = 1024 + p.stages * stage_bytes + bar_bytes;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + epi_bytes + bar_bytes;
 
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -614,14 +776,27 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   CUtensorMap tmA, tmB;
   if (!encode_map(&tmA, A, adims, astr, abox) || !encode_map(&tmB, B, bdims, bstr, bbox)) return A3T_ERR_UNSUPPORTED;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX);
+  // ---- epilogue class -------------------------------------------------------------------------
+  int epi = -1;
+  if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || p.vec_r) &&
+      (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !getenv("A3T_TC_GENERIC_EPI"))
+    epi = (mask ? EPI_MASK : 0) | (d.drop_p > 0.f ? EPI_DROP : 0) | (res ? EPI_RES : 0) |
+          (d.dtype_c == A3T_BF16 ? EPI_BF16 : 0);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+  static const KernelFn table[17] = {
+      gemm_tc_kernel<0>,  gemm_tc_kernel<1>,  gemm_tc_kernel<2>,  gemm_tc_kernel<3>,  gemm_tc_kernel<4>,
+      gemm_tc_kernel<5>,  gemm_tc_kernel<6>,  gemm_tc_kernel<7>,  gemm_tc_kernel<8>,  gemm_tc_kernel<9>,
+      gemm_tc_kernel<10>, gemm_tc_kernel<11>, gemm_tc_kernel<12>, gemm_tc_kernel<13>, gemm_tc_kernel<14>,
+      gemm_tc_kernel<15>, gemm_tc_kernel<-1>};
+  static bool attr_set[17] = {false};
+  const int ki = epi < 0 ? 16 : epi;
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(table[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return A3T_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set[ki] = true;
   }
   if (p.splits > 1) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)d.M * d.sc_m * sizeof(float), st);
@@ -631,7 +806,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
   }
   int grid = p.num_work < sms ? p.num_work : sms;
-  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
+  table[ki]<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
   return check_launch("gemm_tc");
 }
 }  // namespace a3t

@@ -32,16 +32,6 @@ import torch.nn.functional as F
 # --------------------------------------------------------------------------------------
 
 
-def _fmix32(x: np.ndarray) -> np.ndarray:
-    x = x.copy()
-    x ^= x >> np.uint32(16)
-    x *= np.uint32(0x85EBCA6B)
-    x ^= x >> np.uint32(13)
-    x *= np.uint32(0xC2B2AE35)
-    x ^= x >> np.uint32(16)
-    return x
-
-
 def keep_mask(numel: int, p: float, seed: int, site: int) -> torch.Tensor:
     """Bool keep-mask over a contiguous tensor of `numel` elements (True = kept)."""
     if p <= 0.0:
@@ -51,10 +41,13 @@ def keep_mask(numel: int, p: float, seed: int, site: int) -> torch.Tensor:
         lo = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
         hi = (idx >> np.uint64(32)).astype(np.uint32)
         x = lo ^ (hi * np.uint32(0x85EBCA6B))
-        x ^= np.uint32(seed & 0xFFFFFFFF) + np.uint32(site) * np.uint32(0x9E3779B9)
-        x = _fmix32(x)
-        x += np.uint32((seed >> 32) & 0xFFFFFFFF)
-        x = _fmix32(x)
+        k0 = np.uint32(seed & 0xFFFFFFFF) + np.uint32(site) * np.uint32(0x9E3779B9)
+        k1 = np.uint32((seed >> 32) & 0xFFFFFFFF)
+        x = (x ^ k0) * np.uint32(0x9E3779B1) + k1
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x7FEB352D)
+        x ^= x >> np.uint32(15)
+        x *= np.uint32(0x846CA68B)
     thr = np.uint32(np.float32(p) * np.float32(16777216.0))
     return torch.from_numpy((x >> np.uint32(8)) >= thr)
 
