@@ -131,15 +131,172 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
   }
 }
 
-__global__ void dwconv_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                        float* __restrict__ dbias, int nblk, int C, int K) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (K + 1) * C) return;
-  int k = idx / C, c = idx % C;
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time kernel size KT (7 / 15 / 31): each thread owns one channel and DW_TPT consecutive
+// time steps; the DW_TPT + KT - 1 inputs it needs are read from shared memory ONCE into a
+// register window, so the inner loops are pure FMAs (the generic kernels above issue one shared
+// load per FMA and are shared-memory bound).
+// ---------------------------------------------------------------------------------------------
+template <typename TU, int KT>
+__global__ void __launch_bounds__(256) glu_dwconv_fwd_kt_kernel(const TU* __restrict__ u, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ z,
+                                                                int B, int S, int C) {
+  constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2;
+  __shared__ float tile[ROWS][DW_TC];
+  const int ntt = (S + DW_TT - 1) / DW_TT;
+  const int b = blockIdx.x / ntt, t0 = (blockIdx.x % ntt) * DW_TT;
+  const int c0 = blockIdx.y * DW_TC;
+  // GLU of the haloed tile: 2 channels per thread (bf16x2 / float2 loads)
+  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 2); idx += 256) {
+    int rr = idx / (DW_TC / 2), cc = (idx % (DW_TC / 2)) * 2;
+    int t = t0 - pad + rr, c = c0 + cc;
+    float v0 = 0.f, v1 = 0.f;
+    if (t >= 0 && t < S && c < C) {
+      const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
+      float a0 = to_f32<TU>(ur[c]), a1 = to_f32<TU>(ur[c + 1]);
+      float g0 = to_f32<TU>(ur[C + c]), g1 = to_f32<TU>(ur[C + c + 1]);
+      v0 = a0 * sigmoidf_(g0);
+      v1 = a1 * sigmoidf_(g1);
+    }
+    tile[rr][cc] = v0;
+    tile[rr][cc + 1] = v1;
+  }
+  __syncthreads();
+  const int cc = threadIdx.x % DW_TC, tg = threadIdx.x / DW_TC;
+  const int c = c0 + cc;
+  if (c >= C) return;
+  float wk[KT];
+#pragma unroll
+  for (int k = 0; k < KT; k++) wk[k] = w[(int64_t)c * KT + k];
+  const float bv = bias ? bias[c] : 0.f;
+  float win[WIN];
+#pragma unroll
+  for (int i = 0; i < WIN; i++) win[i] = tile[tg * DW_TPT + i][cc];
+#pragma unroll
+  for (int tt = 0; tt < DW_TPT; tt++) {
+    int t = t0 + tg * DW_TPT + tt;
+    float acc = bv;
+#pragma unroll
+    for (int k = 0; k < KT; k++) acc = fmaf(wk[k], win[tt + k], acc);
+    if (t < S) z[((int64_t)b * S + t) * C + c] = acc;
+  }
+}
+
+template <typename TU, typename TDU, int KT>
+__global__ void __launch_bounds__(256) glu_dwconv_bwd_kt_kernel(const float* __restrict__ dz, const TU* __restrict__ u,
+                                                                const float* __restrict__ w, TDU* __restrict__ du,
+                                                                float* __restrict__ partial, int B, int S, int C) {
+  constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2, padr = KT - 1 - pad;
+  __shared__ float smem_raw[2 * ROWS * DW_TC > 4 * (KT + 1) * DW_TC ? 2 * ROWS * DW_TC : 4 * (KT + 1) * DW_TC];
+  float (*tdz)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw);                 // dz, rows from t0-padr
+  float (*tgl)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw + ROWS * DW_TC);  // glu, rows from t0-pad
+  float (*red)[KT + 1][DW_TC] = reinterpret_cast<float (*)[KT + 1][DW_TC]>(smem_raw);  // reused after sync
+  const int ntt = (S + DW_TT - 1) / DW_TT;
+  const int b = blockIdx.x / ntt, t0 = (blockIdx.x % ntt) * DW_TT;
+  const int c0 = blockIdx.y * DW_TC;
+  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 2); idx += 256) {
+    int rr = idx / (DW_TC / 2), cc = (idx % (DW_TC / 2)) * 2;
+    int c = c0 + cc;
+    int t = t0 - padr + rr;
+    float2 dv = make_float2(0.f, 0.f);
+    if (t >= 0 && t < S && c < C) dv = *reinterpret_cast<const float2*>(dz + ((int64_t)b * S + t) * C + c);
+    tdz[rr][cc] = dv.x;
+    tdz[rr][cc + 1] = dv.y;
+    t = t0 - pad + rr;
+    float v0 = 0.f, v1 = 0.f;
+    if (t >= 0 && t < S && c < C) {
+      const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
+      v0 = to_f32<TU>(ur[c]) * sigmoidf_(to_f32<TU>(ur[C + c]));
+      v1 = to_f32<TU>(ur[c + 1]) * sigmoidf_(to_f32<TU>(ur[C + c + 1]));
+    }
+    tgl[rr][cc] = v0;
+    tgl[rr][cc + 1] = v1;
+  }
+  __syncthreads();
+  const int cc = threadIdx.x % DW_TC, tg = threadIdx.x / DW_TC;
+  const int c = c0 + cc;
+  float aw[KT];
+  float ab = 0.f;
+#pragma unroll
+  for (int k = 0; k < KT; k++) aw[k] = 0.f;
+  if (c < C) {
+    float wz[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; i++) wz[i] = tdz[tg * DW_TPT + i][cc];
+    {
+      float wk[KT];
+#pragma unroll
+      for (int k = 0; k < KT; k++) wk[k] = w[(int64_t)c * KT + k];
+      // dglu[t] = sum_k w[k] * dz[t - k + pad]  ->  window index tt + KT - 1 - k
+#pragma unroll
+      for (int tt = 0; tt < DW_TPT; tt++) {
+        int t = t0 + tg * DW_TPT + tt;
+        float dg = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; k++) dg = fmaf(wk[k], wz[tt + KT - 1 - k], dg);
+        if (t < S) {
+          const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
+          float a = to_f32<TU>(ur[c]), g = to_f32<TU>(ur[C + c]);
+          float sg = sigmoidf_(g);
+          TDU* dur = du + ((int64_t)b * S + t) * 2 * C;
+          dur[c] = from_f32<TDU>(dg * sg);
+          dur[C + c] = from_f32<TDU>(dg * a * sg * (1.f - sg));
+        }
+      }
+    }
+    // dw[k] += dz[t] * glu[t + k - pad]: dz[t] = wz[tt + padr] (zero outside the sequence), glu window from tgl
+    float wg[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; i++) wg[i] = tgl[tg * DW_TPT + i][cc];
+#pragma unroll
+    for (int tt = 0; tt < DW_TPT; tt++) {
+      const float dzt = (t0 + tg * DW_TPT + tt < S) ? wz[tt + padr] : 0.f;
+      ab += dzt;
+#pragma unroll
+      for (int k = 0; k < KT; k++) aw[k] = fmaf(dzt, wg[tt + k], aw[k]);
+    }
+  }
+  __syncthreads();  // tiles are dead from here on; reuse them as reduction scratch
+#pragma unroll
+  for (int k = 0; k < KT; k++) red[tg][k][cc] = aw[k];
+  red[tg][KT][cc] = ab;
+  __syncthreads();
+  // partial layout: [blockIdx.x][(K+1)][C]  (row K = dbias)
+  for (int idx = threadIdx.x; idx < (KT + 1) * DW_TC; idx += 256) {
+    int k = idx / DW_TC, c2 = idx % DW_TC;
+    if (c0 + c2 >= C) continue;
+    float t = red[0][k][c2] + red[1][k][c2] + red[2][k][c2] + red[3][k][c2];
+    partial[((int64_t)blockIdx.x * (KT + 1) + k) * C + c0 + c2] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) dwconv_bwd_final_kernel(const float* __restrict__ partial,
+                                                                float* __restrict__ dw, float* __restrict__ dbias,
+                                                                int nblk, int C, int K) {
+  __shared__ float red[8][128];
+  const int col = threadIdx.x & 127, part = threadIdx.x >> 7;
+  const int idx = blockIdx.x * 128 + col;
+  const int n = (K + 1) * C;
   float t = 0.f;
-  for (int b = 0; b < nblk; b++) t += partial[((int64_t)b * (K + 1) + k) * C + c];
-  if (k < K) dw[(int64_t)c * K + k] = t;
-  else if (dbias) dbias[c] = t;
+  if (idx < n) {
+    int b = part;
+    for (; b + 24 < nblk; b += 32) {
+      float t0 = partial[(int64_t)b * n + idx], t1 = partial[(int64_t)(b + 8) * n + idx];
+      float t2 = partial[(int64_t)(b + 16) * n + idx], t3 = partial[(int64_t)(b + 24) * n + idx];
+      t += (t0 + t1) + (t2 + t3);
+    }
+    for (; b < nblk; b += 8) t += partial[(int64_t)b * n + idx];
+  }
+  red[part][col] = t;
+  __syncthreads();
+  if (part == 0 && idx < n) {
+#pragma unroll
+    for (int p2 = 1; p2 < 8; p2++) t += red[p2][col];
+    int k = idx / C, c = idx % C;
+    if (k < K) dw[(int64_t)c * K + k] = t;
+    else if (dbias) dbias[c] = t;
+  }
 }
 
 }  // namespace a3t
@@ -153,7 +310,17 @@ extern "C" int a3t_glu_dwconv_fwd(const void* u, int dtype_u, const float* w, co
   if (B == 0 || S == 0) return A3T_OK;
   dim3 grid(B * ((S + DW_TT - 1) / DW_TT), (C + DW_TC - 1) / DW_TC);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype_u == A3T_BF16)
+#define A3T_DW_FWD(KT)                                                                                          \
+  {                                                                                                             \
+    if (dtype_u == A3T_BF16)                                                                                    \
+      glu_dwconv_fwd_kt_kernel<__nv_bfloat16, KT><<<grid, 256, 0, st>>>((const __nv_bfloat16*)u, w, bias, z, B, S, C); \
+    else                                                                                                        \
+      glu_dwconv_fwd_kt_kernel<float, KT><<<grid, 256, 0, st>>>((const float*)u, w, bias, z, B, S, C);          \
+  }
+  if (k == 7 && C % 2 == 0) A3T_DW_FWD(7)
+  else if (k == 15 && C % 2 == 0) A3T_DW_FWD(15)
+  else if (k == 31 && C % 2 == 0) A3T_DW_FWD(31)
+  else if (dtype_u == A3T_BF16)
     glu_dwconv_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)u, w, bias, z, B, S, C, k);
   else
     glu_dwconv_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)u, w, bias, z, B, S, C, k);
@@ -171,7 +338,19 @@ extern "C" int a3t_glu_dwconv_bwd(const float* dz, const void* u, int dtype_u, c
   int nblk = a3t_dwconv_bwd_blocks(B, S);
   dim3 grid(nblk, (C + DW_TC - 1) / DW_TC);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype_u == A3T_BF16)
+#define A3T_DW_BWD(KT)                                                                                          \
+  {                                                                                                             \
+    if (dtype_u == A3T_BF16)                                                                                    \
+      glu_dwconv_bwd_kt_kernel<__nv_bfloat16, __nv_bfloat16, KT><<<grid, 256, 0, st>>>(                         \
+          dz, (const __nv_bfloat16*)u, w, (__nv_bfloat16*)du, partial, B, S, C);                                \
+    else                                                                                                        \
+      glu_dwconv_bwd_kt_kernel<float, float, KT><<<grid, 256, 0, st>>>(dz, (const float*)u, w, (float*)du,      \
+                                                                      partial, B, S, C);                        \
+  }
+  if (k == 7 && C % 2 == 0) A3T_DW_BWD(7)
+  else if (k == 15 && C % 2 == 0) A3T_DW_BWD(15)
+  else if (k == 31 && C % 2 == 0) A3T_DW_BWD(31)
+  else if (dtype_u == A3T_BF16)
     glu_dwconv_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
         dz, (const __nv_bfloat16*)u, w, (__nv_bfloat16*)du, partial, B, S, C, k);
   else
@@ -179,6 +358,6 @@ extern "C" int a3t_glu_dwconv_bwd(const float* dz, const void* u, int dtype_u, c
   int rc = check_launch("glu_dwconv_bwd");
   if (rc) return rc;
   int n = (k + 1) * C;
-  dwconv_bwd_final_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, dw, dbias, nblk, C, k);
+  dwconv_bwd_final_kernel<<<(n + 127) / 128, 1024, 0, st>>>(partial, dw, dbias, nblk, C, k);
   return check_launch("glu_dwconv_bwd_final");
 }

@@ -157,19 +157,40 @@ int gemm_simt_launch(const A3tGemmDesc* d, const void* A, const void* B, void* C
 }
 
 // weight packing -------------------------------------------------------------------------------
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int N, int C, int taps,
-                                        __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dg) {
-  int64_t total = (int64_t)N * C * taps;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i enumerates the fwd layout (n, tap, c) so the fwd store is coalesced
-    int c = i % C;
-    int64_t r = i / C;
-    int tap = r % taps;
-    int n = r / taps;
-    float v = w[((int64_t)n * C + c) * taps + tap];
-    __nv_bfloat16 bv = __float2bfloat16_rn(v);
-    if (fwd) fwd[i] = bv;
-    if (dg) dg[((int64_t)c * taps + (taps - 1 - tap)) * N + n] = bv;
+// 32 (n) x 32 (c) x taps tile through shared memory: the fp32 read is contiguous in (c, tap), the
+// forward pack is written c-fastest and the dgrad pack n-fastest, so all three streams are coalesced
+// (the first version wrote the dgrad pack with stride N: 21 us per FFN weight instead of ~3).
+constexpr int PK_T = 32;
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int N, int C, int taps,
+                                                               __nv_bfloat16* __restrict__ fwd,
+                                                               __nv_bfloat16* __restrict__ dg) {
+  extern __shared__ float tile[];  // [PK_T][PK_T * taps + 1]
+  const int rowlen = PK_T * taps, ld = rowlen + 1;
+  const int n0 = blockIdx.x * PK_T, c0 = blockIdx.y * PK_T;
+  for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
+    int n = idx / rowlen, j = idx - n * rowlen;
+    int c = c0 + j / taps;
+    float v = 0.f;
+    if (n0 + n < N && c < C) v = w[((int64_t)(n0 + n) * C + c0) * taps + j];
+    tile[n * ld + j] = v;
+  }
+  __syncthreads();
+  if (fwd) {
+    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {  // (n, tap, cc) with cc fastest
+      int cc = idx % PK_T, r = idx / PK_T;
+      int tap = r % taps, n = r / taps;
+      if (n0 + n < N && c0 + cc < C)
+        fwd[(int64_t)(n0 + n) * taps * C + (int64_t)tap * C + c0 + cc] = __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+    }
+  }
+  if (dg) {
+    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {  // (cc, tap, n) with n fastest
+      int n = idx % PK_T, r = idx / PK_T;
+      int tap = r % taps, cc = r / taps;
+      if (n0 + n < N && c0 + cc < C)
+        dg[(int64_t)(c0 + cc) * taps * N + (int64_t)(taps - 1 - tap) * N + n0 + n] =
+            __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+    }
   }
 }
 
@@ -180,10 +201,10 @@ extern "C" int a3t_version(void) { return 100; }
 
 extern "C" int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void* fwd, void* dg, void* stream) {
   A3T_REQUIRE(w && N > 0 && C > 0 && taps > 0, "pack_conv_weight: bad args");
-  int64_t total = (int64_t)N * C * taps;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  a3t::pack_conv_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, N, C, taps, (__nv_bfloat16*)fwd,
-                                                                       (__nv_bfloat16*)dg);
+  A3T_REQUIRE(taps <= 11, "pack_conv_weight: taps=%d too large (max 11)", taps);
+  dim3 grid((N + a3t::PK_T - 1) / a3t::PK_T, (C + a3t::PK_T - 1) / a3t::PK_T);
+  size_t smem = (size_t)a3t::PK_T * (a3t::PK_T * taps + 1) * sizeof(float);
+  a3t::pack_conv_weight_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, N, C, taps, (__nv_bfloat16*)fwd,
+                                                                         (__nv_bfloat16*)dg);
   return a3t::check_launch("pack_conv_weight");
 }

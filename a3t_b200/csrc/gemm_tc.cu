@@ -269,6 +269,7 @@ __device__ __forceinline__ void epilogue4(const Params& p, const Drop& dr, float
 // EPI: -1 = generic epilogue (any strides, WGRAD scatter, split-K atomics); otherwise a bit set
 // EPI_MASK | EPI_DROP | EPI_RES | EPI_BF16 selecting the specialised vectorised epilogue.
 constexpr int EPI_MASK = 1, EPI_DROP = 2, EPI_RES = 4, EPI_BF16 = 8;
+constexpr int EPI_WGRAD = 16;  // fp32 weight-gradient scatter (N, C, taps), optional split-K atomics
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -399,6 +400,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nchunks = (p.block_n + 31) / 32;
     const int rsub = lane >> 3, c4 = lane & 7;
     const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
+    if constexpr (EPI == EPI_WGRAD) {
+      // ---- weight gradient: C[m, (tap, c)] fp32 at m*sc_m + tap*sc_tap + c*sc_n, alpha only ----
+      const float alpha = d.alpha;
+      const bool atomic = p.splits > 1;
+      float* const Cf = (float*)p.C;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const Work t = decode_work(p, w);
+        const int row0 = t.m0 + q * 32 + rsub;
+        bool waited = false, released = false;
+        for (int c = half; c < nchunks; c += 2) {
+          const int col = c * 32 + c4 * 4;
+          const int n4 = t.n0 + col;
+          const bool col_ok = col < p.block_n && n4 < d.cin;
+          if (!waited) {
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + c * 32, acc);
+          tmem_ld_wait();
+          if (c + 2 >= nchunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            released = true;
+          }
+#pragma unroll
+          for (int g4 = 0; g4 < 8; g4++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((g4 ^ (lane & 7)) << 4)),
+                         "r"(acc[4 * g4]), "r"(acc[4 * g4 + 1]), "r"(acc[4 * g4 + 2]), "r"(acc[4 * g4 + 3])
+                         : "memory");
+          __syncwarp();
+          float* const cp0 = Cf + (int64_t)row0 * d.sc_m + (int64_t)t.tap_n * d.sc_tap + (int64_t)n4 * d.sc_n;
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const int R = it * 4 + rsub;
+            float4 a;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                         : "r"(stg + R * 128 + ((c4 ^ (R & 7)) << 4))
+                         : "memory");
+            if (col_ok && (row0 + it * 4) < d.M) {
+              float* cp = cp0 + (int64_t)it * 4 * d.sc_m;
+              const float v[4] = {alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w};
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                if (n4 + j < d.cin) {
+                  if (atomic) atomicAdd(cp + (int64_t)j * d.sc_n, v[j]);
+                  else cp[(int64_t)j * d.sc_n] = v[j];
+                }
+            }
+          }
+          __syncwarp();
+        }
+        if (!waited) {
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+        }
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    } else
     if constexpr (EPI >= 0) {
       // ---- specialised path: PLAIN/CONV, unit column stride, N % 4 == 0, 16-byte aligned rows ----
       constexpr bool kMask = EPI & EPI_MASK, kDrop = EPI & EPI_DROP, kRes = EPI & EPI_RES, kBf16 = EPI & EPI_BF16;
@@ -706,9 +774,13 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   if (mask && d.dtype_mask != A3T_F32 && d.dtype_mask != A3T_BF16) return A3T_ERR_UNSUPPORTED;
   if (probe_only) return get_encode() ? A3T_OK : A3T_ERR_UNSUPPORTED;
 
-  // ---- tile shape: minimise (waves x tile width) over the legal UMMA N values -------------------
+  // ---- tile shape and split-K: minimise  waves x (K iterations per work item) x (bytes staged per K
+  // iteration + a fixed per-iteration cost); the main loop is bound by the shared-memory fill rate ------
   const int sms = num_sms();
-  int best_bn = 0;
+  const bool plain_epi = !bias && !res && !mask && d.drop_p == 0.f && !d.relu;
+  const bool can_split = d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && d.sc_tap == 1 &&
+                         d.sc_n == d.taps && d.sc_m == (int64_t)d.taps * d.cin;
+  int best_bn = 0, best_split = 1;
   double best_cost = 1e30;
   const int cands[5] = {256, 192, 128, 64, ((nlim + 15) / 16) * 16};
   for (int ci = 0; ci < 5; ci++) {
@@ -717,34 +789,28 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     if (p.b_mn && (bn % 64)) continue;
     int nt = ceil_div(nlim, bn) * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
     int64_t tiles = (int64_t)p.m_tiles * nt * nbatch;
-    int64_t waves = (tiles + sms - 1) / sms;
-    double cost = (double)waves * (bn + 24);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+    int max_split = can_split ? (p.k_iters / 16 < 1 ? 1 : p.k_iters / 16) : 1;
+    if (max_split > 32) max_split = 32;
+    for (int sp = 1; sp <= max_split; sp++) {
+      int per = (p.k_iters + sp - 1) / sp;
+      if (sp > 1 && (int64_t)(sp - 1) * per >= p.k_iters) continue;  // would leave an empty split
+      int64_t waves = (tiles * sp + sms - 1) / sms;
+      // per work item: K loop + epilogue (~ tile area), both in units of "bytes staged"
+      double cost = (double)waves * ((double)per * (A_STAGE_BYTES + bn * 128.0 + 4096.0) + 128.0 * bn * (sp > 1 ? 40.0 : 20.0));
+      if (cost < best_cost * 0.999) { best_cost = cost; best_bn = bn; best_split = sp; }
+    }
   }
   if (best_bn == 0) return A3T_ERR_UNSUPPORTED;
   if (const char* e = getenv("A3T_TC_BN")) {  // tuning experiments only
     int v = atoi(e);
-    if (v >= 16 && v <= 256 && v % 16 == 0 && !(p.b_mn && v % 64)) best_bn = v;
+    if (v >= 16 && v <= 256 && v % 16 == 0 && !(p.b_mn && v % 64)) { best_bn = v; best_split = 1; }
   }
   p.block_n = best_bn;
   p.n_tiles_per_tap = ceil_div(nlim, p.block_n);
   p.n_tiles = p.n_tiles_per_tap * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
   int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * nbatch;
-  if (tiles > (1 << 30)) return A3T_ERR_UNSUPPORTED;
-
-  // ---- split-K: only where the output is a small dense fp32 matrix with a plain epilogue ---------
-  p.splits = 1;
-  if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && !bias && !res && !mask && d.drop_p == 0.f && !d.relu &&
-      d.sc_tap == 1 && d.sc_n == d.taps && d.sc_m == (int64_t)d.taps * d.cin && tiles < sms) {
-    int s = (int)(sms / tiles);
-    int maxs = p.k_iters / 8;
-    if (s > maxs) s = maxs;
-    if (s > 1) {
-      int per = (p.k_iters + s - 1) / s;
-      s = (p.k_iters + per - 1) / per;  // no empty split
-      p.splits = s;
-    }
-  }
+  if (tiles * best_split > (1 << 30)) return A3T_ERR_UNSUPPORTED;
+  p.splits = best_split;
   p.num_work = (int)tiles * p.splits;
 
   abox[1] = p.a_mn ? BLOCK_K : BLOCK_M;
@@ -778,18 +844,19 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
 
   // ---- epilogue class -------------------------------------------------------------------------
   int epi = -1;
-  if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || p.vec_r) &&
+  if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && !getenv("A3T_TC_GENERIC_EPI")) epi = EPI_WGRAD;
+  else if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || p.vec_r) &&
       (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !getenv("A3T_TC_GENERIC_EPI"))
     epi = (mask ? EPI_MASK : 0) | (d.drop_p > 0.f ? EPI_DROP : 0) | (res ? EPI_RES : 0) |
           (d.dtype_c == A3T_BF16 ? EPI_BF16 : 0);
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
-  static const KernelFn table[17] = {
+  static const KernelFn table[18] = {
       gemm_tc_kernel<0>,  gemm_tc_kernel<1>,  gemm_tc_kernel<2>,  gemm_tc_kernel<3>,  gemm_tc_kernel<4>,
       gemm_tc_kernel<5>,  gemm_tc_kernel<6>,  gemm_tc_kernel<7>,  gemm_tc_kernel<8>,  gemm_tc_kernel<9>,
       gemm_tc_kernel<10>, gemm_tc_kernel<11>, gemm_tc_kernel<12>, gemm_tc_kernel<13>, gemm_tc_kernel<14>,
-      gemm_tc_kernel<15>, gemm_tc_kernel<-1>};
-  static bool attr_set[17] = {false};
-  const int ki = epi < 0 ? 16 : epi;
+      gemm_tc_kernel<15>, gemm_tc_kernel<EPI_WGRAD>, gemm_tc_kernel<-1>};
+  static bool attr_set[18] = {false};
+  const int ki = epi < 0 ? 17 : epi;
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(table[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX);
     if (e != cudaSuccess) {

@@ -168,13 +168,41 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(
   }
 }
 
-// out[c] = sum_b partial[b*stride + c]  (c < n)
-__global__ void reduce_partial_kernel(const float* __restrict__ partial, float* __restrict__ out0,
-                                      float* __restrict__ out1, int nblk, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
-  float t = 0.f;
-  for (int b = 0; b < nblk; b++) t += partial[(size_t)b * 2 * C + c];
+// Final row reduction shared by every "partial[nblk][n] -> out[n]" step of this file: a block owns 128
+// columns and splits the nblk rows over 8 thread groups (4 independent loads in flight per thread),
+// then combines the 8 partial sums through shared memory.  (The first version walked the rows
+// serially with one thread per column: 10-40 us of pure latency per call.)
+template <typename T>
+__device__ __forceinline__ T reduce_rows_128x8(const T* __restrict__ partial, int nblk, int64_t n, int64_t idx,
+                                               T (*red)[128]) {
+  const int col = threadIdx.x & 127, part = threadIdx.x >> 7;
+  T t = 0;
+  if (idx < n) {
+    int b = part;
+    for (; b + 24 < nblk; b += 32) {
+      T t0 = partial[(int64_t)b * n + idx], t1 = partial[(int64_t)(b + 8) * n + idx];
+      T t2 = partial[(int64_t)(b + 16) * n + idx], t3 = partial[(int64_t)(b + 24) * n + idx];
+      t += (t0 + t1) + (t2 + t3);
+    }
+    for (; b < nblk; b += 8) t += partial[(int64_t)b * n + idx];
+  }
+  red[part][col] = t;
+  __syncthreads();
+  if (part == 0) {
+#pragma unroll
+    for (int p2 = 1; p2 < 8; p2++) t += red[p2][col];
+  }
+  return t;  // valid for part == 0
+}
+
+// out[c] = sum_b partial[b*2C + c]  (c < 2C): first C -> out0, rest -> out1
+__global__ void __launch_bounds__(1024) reduce_partial_kernel(const float* __restrict__ partial,
+                                                              float* __restrict__ out0, float* __restrict__ out1,
+                                                              int nblk, int C) {
+  __shared__ float red[8][128];
+  const int c = blockIdx.x * 128 + (threadIdx.x & 127);
+  float t = reduce_rows_128x8<float>(partial, nblk, 2 * C, c, red);
+  if ((threadIdx.x >> 7) != 0 || c >= 2 * C) return;
   if (c < C) { if (out0) out0[c] = t; }
   else if (out1) out1[c - C] = t;
 }
@@ -200,16 +228,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
   int64_t per = (rows + nblk - 1) / nblk;
   int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per;
   if (r1 > rows) r1 = rows;
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; r++) acc += to_f32<T>(x[r * ldx + c]);
-  partial[(size_t)blockIdx.y * C + c] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {  // 4 independent loads in flight
+    float v0 = to_f32<T>(x[r * ldx + c]), v1 = to_f32<T>(x[(r + 1) * ldx + c]);
+    float v2 = to_f32<T>(x[(r + 2) * ldx + c]), v3 = to_f32<T>(x[(r + 3) * ldx + c]);
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  for (; r < r1; r++) a0 += to_f32<T>(x[r * ldx + c]);
+  partial[(size_t)blockIdx.y * C + c] = (a0 + a1) + (a2 + a3);
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float t = 0.f;
-  for (int b = 0; b < nblk; b++) t += partial[(size_t)b * C + c];
-  out[c] = t;
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int nblk, int C) {
+  __shared__ float red[8][128];
+  const int c = blockIdx.x * 128 + (threadIdx.x & 127);
+  float t = reduce_rows_128x8<float>(partial, nblk, C, c, red);
+  if ((threadIdx.x >> 7) == 0 && c < C) out[c] = t;
 }
 
 // masked column sums for NewMaskInputLayer backward (mlm_encoder.py:67-70)
@@ -262,23 +296,27 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
   partial[((size_t)blockIdx.y * 2) * C + c] = s;
   partial[((size_t)blockIdx.y * 2 + 1) * C + c] = q;
 }
-__global__ void bn_final_kernel(const double* __restrict__ partial, float* __restrict__ mean_o,
-                                float* __restrict__ rstd_o, float* __restrict__ running_mean,
-                                float* __restrict__ running_var, int64_t* __restrict__ nbt, int nblk,
-                                int64_t rows, int C, float momentum, float eps, int training) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && nbt) *nbt += 1;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024) bn_final_kernel(const double* __restrict__ partial, float* __restrict__ mean_o,
+                                                        float* __restrict__ rstd_o, float* __restrict__ running_mean,
+                                                        float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                                        int nblk, int64_t rows, int C, float momentum, float eps,
+                                                        int training) {
+  __shared__ double red[8][128];
+  const int c = blockIdx.x * 128 + (threadIdx.x & 127);
+  const bool lead = (threadIdx.x >> 7) == 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
   if (!training) {
-    mean_o[c] = running_mean[c];
-    rstd_o[c] = rsqrtf(running_var[c] + eps);
+    if (lead && c < C) {
+      mean_o[c] = running_mean[c];
+      rstd_o[c] = rsqrtf(running_var[c] + eps);
+    }
     return;
   }
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; b++) {
-    s += partial[((size_t)b * 2) * C + c];
-    q += partial[((size_t)b * 2 + 1) * C + c];
-  }
+  // partial rows alternate [sum | sum of squares] with row length C: view as nblk rows of 2C
+  double s = reduce_rows_128x8<double>(partial, nblk, 2 * (int64_t)C, c < C ? c : (int64_t)2 * C, red);
+  __syncthreads();
+  double q = reduce_rows_128x8<double>(partial, nblk, 2 * (int64_t)C, c < C ? (int64_t)C + c : (int64_t)2 * C, red);
+  if (!lead || c >= C) return;
   double n = (double)rows;
   double mean = s / n;
   double var = q / n - mean * mean;
@@ -361,15 +399,15 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
   partial[((size_t)blockIdx.y * 2) * C + c] = sb;
   partial[((size_t)blockIdx.y * 2 + 1) * C + c] = sg;
 }
-__global__ void bn_bwd_final_kernel(const double* __restrict__ partial, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, float* __restrict__ coef, int nblk, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sb = 0.0, sg = 0.0;
-  for (int b = 0; b < nblk; b++) {
-    sb += partial[((size_t)b * 2) * C + c];
-    sg += partial[((size_t)b * 2 + 1) * C + c];
-  }
+__global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const double* __restrict__ partial,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ coef, int nblk, int C) {
+  __shared__ double red[8][128];
+  const int c = blockIdx.x * 128 + (threadIdx.x & 127);
+  double sb = reduce_rows_128x8<double>(partial, nblk, 2 * (int64_t)C, c < C ? c : (int64_t)2 * C, red);
+  __syncthreads();
+  double sg = reduce_rows_128x8<double>(partial, nblk, 2 * (int64_t)C, c < C ? (int64_t)C + c : (int64_t)2 * C, red);
+  if ((threadIdx.x >> 7) != 0 || c >= C) return;
   dbeta[c] = (float)sb;
   dgamma[c] = (float)sg;
   coef[c] = (float)sb;
@@ -456,7 +494,7 @@ extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, c
   int rc = check_launch("layernorm_bwd");
   if (rc) return rc;
   if (dgamma || dbeta) {
-    reduce_partial_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, dgamma, dbeta, nblk, C);
+    reduce_partial_kernel<<<(2 * C + 127) / 128, 1024, 0, st>>>(partial, dgamma, dbeta, nblk, C);
     rc = check_launch("layernorm_bwd_reduce");
   }
   return rc;
@@ -476,7 +514,7 @@ extern "C" int a3t_colsum(const void* x, int dtype_x, float* out, float* partial
     colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, partial, rows, C, ldx);
   int rc = check_launch("colsum");
   if (rc) return rc;
-  colsum_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, out, nblk, C);
+  colsum_final_kernel<<<(C + 127) / 128, 1024, 0, st>>>(partial, out, nblk, C);
   return check_launch("colsum_final");
 }
 
@@ -502,7 +540,7 @@ extern "C" int a3t_mask_input_bwd(const float* dx, const uint8_t* masked, float*
   masked_colsum_kernel<<<grid, 256, 0, st>>>(dx, masked, partial, rows, C);
   int rc = check_launch("mask_input_bwd");
   if (rc) return rc;
-  colsum_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, dmask_feature, nblk, C);
+  colsum_final_kernel<<<(C + 127) / 128, 1024, 0, st>>>(partial, dmask_feature, nblk, C);
   return check_launch("mask_input_bwd_final");
 }
 
@@ -519,7 +557,7 @@ extern "C" int a3t_bn_stats(const float* z, float* mean, float* rstd, float* run
     int rc = check_launch("bn_partial");
     if (rc) return rc;
   }
-  bn_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, mean, rstd, running_mean, running_var,
+  bn_final_kernel<<<(C + 127) / 128, 1024, 0, st>>>(partial, mean, rstd, running_mean, running_var,
                                                    num_batches_tracked, nblk, rows, C, momentum, eps, training);
   return check_launch("bn_final");
 }
@@ -554,7 +592,7 @@ extern "C" int a3t_bn_act_bwd(const float* dy, const float* z, const float* mean
   bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, partial, rows, C, act, drop_p, seed, site);
   int rc = check_launch("bn_bwd_partial");
   if (rc) return rc;
-  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, dgamma, dbeta, coef, nblk, C);
+  bn_bwd_final_kernel<<<(C + 127) / 128, 1024, 0, st>>>(partial, dgamma, dbeta, coef, nblk, C);
   rc = check_launch("bn_bwd_final");
   if (rc) return rc;
   int64_t n = rows * C;
