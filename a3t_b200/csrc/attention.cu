@@ -102,6 +102,158 @@ __global__ void __launch_bounds__(256) relshift_bwd_kernel(const TO* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised kernels for S % 4 == 0.  A lane owns 4 consecutive keys per step (float4 loads of AC /
+// dPd, 8-byte bf16 stores).  rel_shift without integer division: for query row i
+//   shifted[i, j] = BD_raw[i, S-1-i+j] (j <= i) | 0 (j == i+1) | BD_raw[i+1, j-i-2] (j >= i+2)
+// which is transformer/attention.py:155-159 written out (pad one zero column, view (S+1, S), drop row 0).
+// ---------------------------------------------------------------------------------------------
+template <typename TP>
+__device__ __forceinline__ void store_p4(TP* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_p4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store_p4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 h[2] = {__floats2bfloat162_rn(a, b), __floats2bfloat162_rn(c, d)};
+  *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(h);
+}
+template <typename TP>
+__device__ __forceinline__ void load_p4(const TP* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load_p4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load_p4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
+    const float* __restrict__ ac, const float* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
+    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    const unsigned long long* __restrict__ seed, uint32_t site) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* row = sm + (size_t)warp * S;
+  Drop dr = make_drop(drop_p, seed, site);
+  const int64_t nrows = (int64_t)B * H * S;
+  for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
+    const int i = (int)(r % S);
+    const int64_t bh = r / S;
+    const int b = (int)(bh / H);
+    const float* acr = ac + r * S;
+    const float* bd0 = bd_raw + (bh * S + i) * (int64_t)S + (S - 1 - i);   // + j       for j <= i
+    const float* bd1 = bd_raw + (bh * S + i + 1) * (int64_t)S - (i + 2);   // + j       for j >= i+2
+    const uint8_t* km = keymask + (int64_t)b * S;
+    float mx = -FLT_MAX;
+    for (int j = lane * 4; j < S; j += 128) {
+      const float4 a4 = *reinterpret_cast<const float4*>(acr + j);
+      const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const unsigned char kk[4] = {k4.x, k4.y, k4.z, k4.w};
+      float sv[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int jj = j + e;
+        float bd = 0.f;
+        if (jj <= i) bd = bd0[jj];
+        else if (jj >= i + 2) bd = bd1[jj];
+        float v = (a[e] + bd) * scale;
+        if (!kk[e]) v = -FLT_MAX;  // finfo(float32).min
+        sv[e] = v;
+        mx = fmaxf(mx, v);
+      }
+      *reinterpret_cast<float4*>(row + j) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane * 4; j < S; j += 128) {
+      float4 t = *reinterpret_cast<float4*>(row + j);
+      t.x = __expf(t.x - mx); t.y = __expf(t.y - mx); t.z = __expf(t.z - mx); t.w = __expf(t.w - mx);
+      sum += (t.x + t.y) + (t.z + t.w);
+      *reinterpret_cast<float4*>(row + j) = t;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane * 4; j < S; j += 128) {
+      const float4 t = *reinterpret_cast<float4*>(row + j);
+      const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
+      float pv[4] = {k4.x ? t.x * inv : 0.f, k4.y ? t.y * inv : 0.f, k4.z ? t.z * inv : 0.f, k4.w ? t.w * inv : 0.f};
+      store_p4<TP>(P + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+      if (dr.on) {
+        const unsigned long long idx0 = (unsigned long long)(r * S + j);
+        const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+        for (int e = 0; e < 4; e++) pv[e] = drop_keep32(dr, (lo + e) ^ hif) ? pv[e] * dr.inv_keep : 0.f;
+        store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+      } else if (Pd != P) {
+        store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// dS = P * (dPu - sum_j dPu*P) * scale, and dBD_raw = inverse rel_shift of dS written by the same warp:
+//   row i of dS feeds dBD[i, S-1-i+j] (j <= i) and dBD[i+1, j-i-2] (j >= i+2); row 0 of dBD is zero
+//   except its last element.  Every dBD element is written exactly once.
+template <typename TP, typename TO>
+__global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
+    const float* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nrows,
+    int S, float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* row = sm + (size_t)warp * S;
+  Drop dr = make_drop(drop_p, seed, site);
+  for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
+    const int i = (int)(r % S);
+    float dot = 0.f;
+    for (int j = lane * 4; j < S; j += 128) {
+      const float4 g4 = *reinterpret_cast<const float4*>(dPd + r * S + j);
+      float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      float pv[4];
+      load_p4<TP>(P + r * S + j, pv);
+      if (dr.on) {
+        const unsigned long long idx0 = (unsigned long long)(r * S + j);
+        const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+        for (int e = 0; e < 4; e++) g[e] = drop_keep32(dr, (lo + e) ^ hif) ? g[e] * dr.inv_keep : 0.f;
+      }
+      dot += (g[0] * pv[0] + g[1] * pv[1]) + (g[2] * pv[2] + g[3] * pv[3]);
+      *reinterpret_cast<float4*>(row + j) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    dot = warp_sum(dot);
+    TO* d0 = dBD + r * S + (S - 1 - i);          // + j   for j <= i
+    TO* d1 = dBD + (r + 1) * S - (i + 2);        // + j   for j >= i+2 (row i+1 of the same matrix)
+    for (int j = lane * 4; j < S; j += 128) {
+      float pv[4];
+      load_p4<TP>(P + r * S + j, pv);
+      const float4 g4 = *reinterpret_cast<float4*>(row + j);
+      const float o[4] = {pv[0] * (g4.x - dot) * scale, pv[1] * (g4.y - dot) * scale, pv[2] * (g4.z - dot) * scale,
+                          pv[3] * (g4.w - dot) * scale};
+      store_p4<TO>(dS + r * S + j, o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int jj = j + e;
+        if (jj <= i) d0[jj] = from_f32<TO>(o[e]);
+        else if (jj >= i + 2 && i + 1 < S) d1[jj] = from_f32<TO>(o[e]);
+      }
+    }
+    if (i == 0) {  // BD_raw[0, 0..S-2] is never read by the forward
+      for (int j = lane; j < S - 1; j += 32) dBD[r * S + j] = from_f32<TO>(0.f);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace a3t
 
 using namespace a3t;
@@ -117,6 +269,16 @@ extern "C" int a3t_relpos_softmax_fwd(const float* ac, const float* bd_raw, cons
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
+  const bool v4 = (S % 4) == 0 && ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
+  if (v4 && smem <= 48 * 1024) {
+    if (dtype_p == A3T_BF16)
+      relpos_softmax_fwd_v4_kernel<__nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
+          ac, bd_raw, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
+    else
+      relpos_softmax_fwd_v4_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, keymask, (float*)P,
+                                                                              (float*)Pd, B, H, S, scale, drop_p, seed, site);
+    return check_launch("relpos_softmax_fwd");
+  }
   if (dtype_p == A3T_BF16) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(relpos_softmax_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -138,6 +300,11 @@ static int softmax_bwd_launch(const float* dPd, const void* P, void* dS, void* d
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
+  if ((S % 4) == 0 && smem <= 48 * 1024 && ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0)) {
+    relpos_softmax_bwd_v4_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows,
+                                                                             S, scale, drop_p, seed, site);
+    return check_launch("relpos_softmax_bwd");
+  }
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(relpos_softmax_bwd_kernel<TP, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, (const TP*)P, (TO*)dS, nrows, S, scale,

@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(
 // LayerNorm backward: warp per row; per-lane dgamma/dbeta register accumulators, block-reduced
 // into partial[blk][2][C]; a second kernel finishes the column sums.
 // ---------------------------------------------------------------------------------------------
-template <typename TDY>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(
+template <typename TDY, int MAXV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
     const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ dres, float* __restrict__ dx, float* __restrict__ partial, int64_t rows,
@@ -85,55 +85,68 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = C >> 2;
   Drop dr = make_drop(drop_p, seed, site);
-  float4 ag[LN_MAXV], ab[LN_MAXV], gm[LN_MAXV], bt[LN_MAXV];
+  float4 ag[MAXV], ab[MAXV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < MAXV; i++) {
     ag[i] = make_float4(0, 0, 0, 0);
     ab[i] = make_float4(0, 0, 0, 0);
-    int c4 = lane + i * 32;
-    if (c4 < nv) {
-      gm[i] = reinterpret_cast<const float4*>(gamma)[c4];
-      bt[i] = reinterpret_cast<const float4*>(beta)[c4];
-    }
   }
   const float scale_keep = out_scale * dr.inv_keep;
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LN_WARPS) {
     const float mean = mean_i[row], rstd = rstd_i[row];
-    float xh[LN_MAXV][4], dh[LN_MAXV][4];
+    float xh[MAXV][4], dh[MAXV][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       int c4 = lane + i * 32;
       if (c4 < nv) {
-        float4 xv = reinterpret_cast<const float4*>(x + row * C)[c4];
-        float xe[4] = {xv.x, xv.y, xv.z, xv.w};
-        float ge[4] = {gm[i].x, gm[i].y, gm[i].z, gm[i].w};
-        float be[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
-        float gacc[4], bacc[4];
+        const float4 xv = reinterpret_cast<const float4*>(x + row * C)[c4];
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident: not kept in registers
+        const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+        float g[4];
+        const int64_t idx0 = row * C + c4 * 4;
+        if constexpr (sizeof(TDY) == 2) {
+          const uint2 t = *reinterpret_cast<const uint2*>(dy + idx0);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+          float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+          g[0] = f0.x; g[1] = f0.y; g[2] = f1.x; g[3] = f1.y;
+        } else {
+          const float4 t = *reinterpret_cast<const float4*>(dy + idx0);
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+        }
+        if (dr.on) {
+          const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)((unsigned long long)idx0 >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[e] = drop_keep32(dr, (lo + e) ^ hif) ? g[e] : 0.f;
+        }
+        float be[4] = {0.f, 0.f, 0.f, 0.f};
+        if (relu) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+          be[0] = bv.x; be[1] = bv.y; be[2] = bv.z; be[3] = bv.w;
+        }
+        float gacc[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          int64_t idx = row * C + c4 * 4 + e;
-          float g = to_f32<TDY>(dy[idx]);
-          if (dr.on) g = drop_keep(dr, (unsigned long long)idx) ? g : 0.f;
-          g *= scale_keep;
+          float ge_ = g[e] * scale_keep;
           float h = (xe[e] - mean) * rstd;
-          if (relu && (h * ge[e] + be[e]) <= 0.f) g = 0.f;
+          if (relu && (h * ge[e] + be[e]) <= 0.f) ge_ = 0.f;
           xh[i][e] = h;
-          gacc[e] = g * h;
-          bacc[e] = g;
-          float d = g * ge[e];
+          gacc[e] = ge_ * h;
+          g[e] = ge_;
+          float d = ge_ * ge[e];
           dh[i][e] = d;
           s1 += d;
           s2 += d * h;
         }
         ag[i].x += gacc[0]; ag[i].y += gacc[1]; ag[i].z += gacc[2]; ag[i].w += gacc[3];
-        ab[i].x += bacc[0]; ab[i].y += bacc[1]; ab[i].z += bacc[2]; ab[i].w += bacc[3];
+        ab[i].x += g[0]; ab[i].y += g[1]; ab[i].z += g[2]; ab[i].w += g[3];
       }
     }
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < MAXV; i++) {
       int c4 = lane + i * 32;
       if (c4 < nv) {
         float4 o;
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(
   // block reduce the parameter gradients
   float* sg = sm + (size_t)warp * 2 * C;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < MAXV; i++) {
     int c4 = lane + i * 32;
     if (c4 < nv) {
       reinterpret_cast<float4*>(sg)[c4] = ag[i];
@@ -246,6 +259,77 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   if ((threadIdx.x >> 7) == 0 && c < C) out[c] = t;
 }
 
+// Vectorised variant: a thread owns 4 (fp32) or 8 (bf16) consecutive columns = one 16-byte load per
+// row; a block is 32 column groups x 8 row lanes (a warp reads 512 contiguous bytes of a row), rows
+// unrolled by 4 for memory-level parallelism; the 8 row lanes are combined through shared memory.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ partial,
+                                                         int64_t rows, int C, int64_t ldx) {
+  constexpr int N = Vec16<T>::N;
+  __shared__ float red[8][32 * N + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * N;
+  const int nblk = gridDim.y;
+  const int64_t per = (rows + nblk - 1) / nblk;
+  const int64_t r0 = (int64_t)blockIdx.y * per;
+  int64_t r1 = r0 + per;
+  if (r1 > rows) r1 = rows;
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) acc[i] = 0.f;
+  if (c < C) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float v0[N], v1[N], v2[N], v3[N];
+      Vec16<T>::load(x + r * ldx + c, v0);
+      Vec16<T>::load(x + (r + 8) * ldx + c, v1);
+      Vec16<T>::load(x + (r + 16) * ldx + c, v2);
+      Vec16<T>::load(x + (r + 24) * ldx + c, v3);
+#pragma unroll
+      for (int i = 0; i < N; i++) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+    }
+    for (; r < r1; r += 8) {
+      float v0[N];
+      Vec16<T>::load(x + r * ldx + c, v0);
+#pragma unroll
+      for (int i = 0; i < N; i++) acc[i] += v0[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) red[ty][tx * N + i] = acc[i];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
+    int cc = blockIdx.x * 32 * N + idx;
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; y++) t += red[y][idx];
+      partial[(size_t)blockIdx.y * C + cc] = t;
+    }
+  }
+}
+
 // masked column sums for NewMaskInputLayer backward (mlm_encoder.py:67-70)
 __global__ void __launch_bounds__(256) masked_colsum_kernel(const float* __restrict__ x,
                                                             const uint8_t* __restrict__ masked,
@@ -266,35 +350,89 @@ __global__ void __launch_bounds__(256) masked_colsum_kernel(const float* __restr
 // scale + dropout elementwise
 // ---------------------------------------------------------------------------------------------
 template <typename TY>
+__device__ __forceinline__ void store4(TY* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v[0], v[1]), __floats2bfloat162_rn(v[2], v[3])};
+  *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(h);
+}
+// keep-mask of 4 consecutive elements starting at idx0 (idx0 % 4 == 0)
+__device__ __forceinline__ void drop_apply4(const Drop& dr, unsigned long long idx0, float (&v)[4]) {
+  if (!dr.on) return;
+  const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * dr.inv_keep : 0.f;
+}
+
+template <typename TY>
 __global__ void __launch_bounds__(256) scale_dropout_kernel(const float* __restrict__ x, TY* __restrict__ y,
                                                             int64_t n, float scale, float drop_p,
                                                             const unsigned long long* __restrict__ seed,
                                                             uint32_t site) {
   Drop dr = make_drop(drop_p, seed, site);
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 t = reinterpret_cast<const float4*>(x)[i];
+    float v[4] = {t.x * scale, t.y * scale, t.z * scale, t.w * scale};
+    drop_apply4(dr, (unsigned long long)i * 4ull, v);
+    store4<TY>(y + i * 4, v);
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = from_f32<TY>(drop_apply(dr, (unsigned long long)i, x[i] * scale));
 }
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm1d statistics: double column sums of z and z^2
 // ---------------------------------------------------------------------------------------------
+// block = 32 column groups (4 channels each) x 8 row lanes; fp32 partial sums over <= 16 rows are
+// promoted to double before they are combined (the reference accumulates in fp32; double keeps the
+// batch statistics independent of the blocking)
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, double* __restrict__ partial,
                                                          int64_t rows, int C) {
-  int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
-  int nblk = gridDim.y;
-  int64_t per = (rows + nblk - 1) / nblk;
-  int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per;
+  __shared__ double red[8][2][128 + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 4;
+  const int nblk = gridDim.y;
+  const int64_t per = (rows + nblk - 1) / nblk;
+  const int64_t r0 = (int64_t)blockIdx.y * per;
+  int64_t r1 = r0 + per;
   if (r1 > rows) r1 = rows;
-  double s = 0.0, q = 0.0;
-  for (int64_t r = r0; r < r1; r++) {
-    double v = (double)z[r * C + c];
-    s += v;
-    q += v * v;
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (c < C) {
+    for (int64_t rb = r0 + ty; rb < r1; rb += 8 * 16) {
+      float fs[4] = {0, 0, 0, 0}, fq[4] = {0, 0, 0, 0};
+#pragma unroll 4
+      for (int k = 0; k < 16; k++) {
+        int64_t r = rb + (int64_t)k * 8;
+        if (r < r1) {
+          float4 t = *reinterpret_cast<const float4*>(z + r * C + c);
+          fs[0] += t.x; fs[1] += t.y; fs[2] += t.z; fs[3] += t.w;
+          fq[0] = fmaf(t.x, t.x, fq[0]); fq[1] = fmaf(t.y, t.y, fq[1]);
+          fq[2] = fmaf(t.z, t.z, fq[2]); fq[3] = fmaf(t.w, t.w, fq[3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) { s[i] += (double)fs[i]; q[i] += (double)fq[i]; }
+    }
   }
-  partial[((size_t)blockIdx.y * 2) * C + c] = s;
-  partial[((size_t)blockIdx.y * 2 + 1) * C + c] = q;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { red[ty][0][tx * 4 + i] = s[i]; red[ty][1][tx * 4 + i] = q[i]; }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * 128; idx += 256) {
+    int which = idx >> 7, cc = idx & 127;
+    int col = blockIdx.x * 128 + cc;
+    if (col < C) {
+      double t = 0;
+#pragma unroll
+      for (int y = 0; y < 8; y++) t += red[y][which][cc];
+      partial[((size_t)blockIdx.y * 2 + which) * C + col] = t;
+    }
+  }
 }
 __global__ void __launch_bounds__(1024) bn_final_kernel(const double* __restrict__ partial, float* __restrict__ mean_o,
                                                         float* __restrict__ rstd_o, float* __restrict__ running_mean,
@@ -356,15 +494,24 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
                                                          int64_t rows, int C, int act, float drop_p,
                                                          const unsigned long long* __restrict__ seed, uint32_t site) {
   Drop dr = make_drop(drop_p, seed, site);
-  int64_t n = rows * C;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int c = (int)(i % C);
-    float v = (z[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-    v = act_fwd(v, act);
-    v = drop_apply(dr, (unsigned long long)i, v);
-    if (res) v += res[i];
-    y[i] = from_f32<TY>(v);
+  const int C4 = C >> 2;
+  const int64_t n4 = rows * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const float4 zz = reinterpret_cast<const float4*>(z)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float v[4] = {(zz.x - mu.x) * rs.x * g.x + b.x, (zz.y - mu.y) * rs.y * g.y + b.y,
+                  (zz.z - mu.z) * rs.z * g.z + b.z, (zz.w - mu.w) * rs.w * g.w + b.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = act_fwd(v[j], act);
+    drop_apply4(dr, (unsigned long long)i * 4ull, v);
+    if (res) {
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    store4<TY>(y + i * 4, v);
   }
 }
 
@@ -378,26 +525,59 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
                                                              int act, float drop_p,
                                                              const unsigned long long* __restrict__ seed,
                                                              uint32_t site) {
-  int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[8][2][128 + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 4;
   Drop dr = make_drop(drop_p, seed, site);
-  int nblk = gridDim.y;
-  int64_t per = (rows + nblk - 1) / nblk;
-  int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per;
+  const int nblk = gridDim.y;
+  const int64_t per = (rows + nblk - 1) / nblk;
+  const int64_t r0 = (int64_t)blockIdx.y * per;
+  int64_t r1 = r0 + per;
   if (r1 > rows) r1 = rows;
-  const float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
-  double sb = 0.0, sg = 0.0;
-  for (int64_t r = r0; r < r1; r++) {
-    int64_t i = r * C + c;
-    float zh = (z[i] - mu) * rs;
-    float d = dy[i];
-    if (dr.on) d = drop_keep(dr, (unsigned long long)i) ? d * dr.inv_keep : 0.f;
-    d *= act_grad(zh * g + b, act);
-    sb += (double)d;
-    sg += (double)d * (double)zh;
+  double sb[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0};
+  if (c < C) {
+    const float4 mu4 = *reinterpret_cast<const float4*>(mean + c), rs4 = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + c), b4 = *reinterpret_cast<const float4*>(beta + c);
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int64_t rb = r0 + ty; rb < r1; rb += 8 * 16) {
+      float fb[4] = {0, 0, 0, 0}, fg[4] = {0, 0, 0, 0};
+#pragma unroll 2
+      for (int k = 0; k < 16; k++) {
+        int64_t r = rb + (int64_t)k * 8;
+        if (r < r1) {
+          const int64_t i = r * C + c;
+          const float4 z4 = *reinterpret_cast<const float4*>(z + i);
+          const float4 d4 = *reinterpret_cast<const float4*>(dy + i);
+          const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+          float d[4] = {d4.x, d4.y, d4.z, d4.w};
+          drop_apply4(dr, (unsigned long long)i, d);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float zh = (zz[j] - mu[j]) * rs[j];
+            float dd = d[j] * act_grad(zh * g[j] + b[j], act);
+            fb[j] += dd;
+            fg[j] = fmaf(dd, zh, fg[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) { sb[j] += (double)fb[j]; sg[j] += (double)fg[j]; }
+    }
   }
-  partial[((size_t)blockIdx.y * 2) * C + c] = sb;
-  partial[((size_t)blockIdx.y * 2 + 1) * C + c] = sg;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { red[ty][0][tx * 4 + i] = sb[i]; red[ty][1][tx * 4 + i] = sg[i]; }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * 128; idx += 256) {
+    int which = idx >> 7, cc = idx & 127;
+    int col = blockIdx.x * 128 + cc;
+    if (col < C) {
+      double t = 0;
+#pragma unroll
+      for (int y = 0; y < 8; y++) t += red[y][which][cc];
+      partial[((size_t)blockIdx.y * 2 + which) * C + col] = t;
+    }
+  }
 }
 __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const double* __restrict__ partial,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -420,19 +600,28 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict_
                                                         int64_t rows, int C, int act, int training, float drop_p,
                                                         const unsigned long long* __restrict__ seed, uint32_t site) {
   Drop dr = make_drop(drop_p, seed, site);
-  int64_t n = rows * C;
+  const int C4 = C >> 2;
+  const int64_t n4 = rows * C4;
   const float inv_n = 1.f / (float)rows;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int c = (int)(i % C);
-    float zh = (z[i] - mean[c]) * rstd[c];
-    float d = dy[i];
-    if (dr.on) d = drop_keep(dr, (unsigned long long)i) ? d * dr.inv_keep : 0.f;
-    d *= act_grad(zh * gamma[c] + beta[c], act);
-    float o;
-    if (training) o = gamma[c] * rstd[c] * (d - coef[c] * inv_n - zh * coef[C + c] * inv_n);
-    else o = gamma[c] * rstd[c] * d;
-    dz[i] = o;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const float4 z4 = reinterpret_cast<const float4*>(z)[i], d4 = reinterpret_cast<const float4*>(dy)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    const float4 k0 = *reinterpret_cast<const float4*>(coef + c), k1 = *reinterpret_cast<const float4*>(coef + C + c);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, mm[4] = {mu.x, mu.y, mu.z, mu.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+    const float c0[4] = {k0.x, k0.y, k0.z, k0.w}, c1[4] = {k1.x, k1.y, k1.z, k1.w};
+    float d[4] = {d4.x, d4.y, d4.z, d4.w}, o[4];
+    drop_apply4(dr, (unsigned long long)i * 4ull, d);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float zh = (zz[j] - mm[j]) * rr[j];
+      float dd = d[j] * act_grad(zh * gg[j] + bb[j], act);
+      o[j] = training ? gg[j] * rr[j] * (dd - c0[j] * inv_n - zh * c1[j] * inv_n) : gg[j] * rr[j] * dd;
+    }
+    reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -469,7 +658,7 @@ extern "C" int a3t_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int a3t_layernorm_bwd_blocks(int64_t rows) {
   int64_t b = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
-  if (b > 148 * 2) b = 148 * 2;
+  if (b > 148 * 3) b = 148 * 3;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -484,13 +673,16 @@ extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, c
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = a3t_layernorm_bwd_blocks(rows);
   size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
-  if (dtype_dy == A3T_BF16)
-    ln_bwd_kernel<__nv_bfloat16><<<nblk, LN_WARPS * 32, smem, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, gamma,
-                                                                   beta, dres, dx, partial, rows, C, relu, out_scale,
-                                                                   drop_p, seed, site);
-  else
-    ln_bwd_kernel<float><<<nblk, LN_WARPS * 32, smem, st>>>((const float*)dy, x, mean, rstd, gamma, beta, dres, dx,
-                                                           partial, rows, C, relu, out_scale, drop_p, seed, site);
+#define A3T_LN_BWD(T, MV)                                                                                          \
+  ln_bwd_kernel<T, MV><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx, partial, \
+                                                          rows, C, relu, out_scale, drop_p, seed, site)
+  if (dtype_dy == A3T_BF16) {
+    if (C <= 384) A3T_LN_BWD(__nv_bfloat16, 3);
+    else A3T_LN_BWD(__nv_bfloat16, 4);
+  } else {
+    if (C <= 384) A3T_LN_BWD(float, 3);
+    else A3T_LN_BWD(float, 4);
+  }
   int rc = check_launch("layernorm_bwd");
   if (rc) return rc;
   if (dgamma || dbeta) {
@@ -508,7 +700,14 @@ extern "C" int a3t_colsum(const void* x, int dtype_x, float* out, float* partial
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = colsum_blocks_host(rows);
   dim3 grid((C + 255) / 256, nblk);
-  if (dtype_x == A3T_BF16)
+  const int vn = dtype_x == A3T_BF16 ? 8 : 4;
+  if (C % vn == 0 && ldx % vn == 0 && ((uintptr_t)x & 15) == 0) {
+    dim3 gv((C / vn + 31) / 32, nblk);
+    if (dtype_x == A3T_BF16)
+      colsum_vec_kernel<__nv_bfloat16><<<gv, 256, 0, st>>>((const __nv_bfloat16*)x, partial, rows, C, ldx);
+    else
+      colsum_vec_kernel<float><<<gv, 256, 0, st>>>((const float*)x, partial, rows, C, ldx);
+  } else if (dtype_x == A3T_BF16)
     colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, partial, rows, C, ldx);
   else
     colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, partial, rows, C, ldx);
@@ -521,13 +720,14 @@ extern "C" int a3t_colsum(const void* x, int dtype_x, float* out, float* partial
 extern "C" int a3t_scale_dropout(const float* x, void* y, int dtype_y, int64_t n, float scale, float drop_p,
                                  const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(x && y, "scale_dropout: null pointer");
+  A3T_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "scale_dropout: buffers must be 16-byte aligned");
   A3T_REQUIRE(drop_p == 0.f || seed, "scale_dropout: dropout needs a seed");
   if (n == 0) return A3T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_y == A3T_BF16)
-    scale_dropout_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(x, (__nv_bfloat16*)y, n, scale, drop_p, seed, site);
+    scale_dropout_kernel<__nv_bfloat16><<<ew_blocks((n + 3) / 4), 256, 0, st>>>(x, (__nv_bfloat16*)y, n, scale, drop_p, seed, site);
   else
-    scale_dropout_kernel<float><<<ew_blocks(n), 256, 0, st>>>(x, (float*)y, n, scale, drop_p, seed, site);
+    scale_dropout_kernel<float><<<ew_blocks((n + 3) / 4), 256, 0, st>>>(x, (float*)y, n, scale, drop_p, seed, site);
   return check_launch("scale_dropout");
 }
 
@@ -548,11 +748,12 @@ extern "C" int a3t_bn_stats(const float* z, float* mean, float* rstd, float* run
                             int64_t* num_batches_tracked, double* partial, int64_t rows, int C, float momentum,
                             float eps, int training, void* stream) {
   A3T_REQUIRE(z && mean && rstd, "bn_stats: null pointer");
+  A3T_REQUIRE(C % 4 == 0, "bn_stats: C=%d must be a multiple of 4", C);
   A3T_REQUIRE(training ? partial != nullptr : (running_mean && running_var), "bn_stats: missing buffers");
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = colsum_blocks_host(rows);
   if (training) {
-    dim3 grid((C + 255) / 256, nblk);
+    dim3 grid((C + 127) / 128, nblk);
     bn_partial_kernel<<<grid, 256, 0, st>>>(z, partial, rows, C);
     int rc = check_launch("bn_partial");
     if (rc) return rc;
@@ -566,15 +767,16 @@ extern "C" int a3t_bn_act_fwd(const float* z, const float* mean, const float* rs
                               const float* beta, const float* res, void* y, int dtype_y, int64_t rows, int C, int act,
                               float drop_p, const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(z && mean && rstd && gamma && beta && y, "bn_act_fwd: null pointer");
+  A3T_REQUIRE(C % 4 == 0, "bn_act_fwd: C=%d must be a multiple of 4", C);
   A3T_REQUIRE(drop_p == 0.f || seed, "bn_act_fwd: dropout needs a seed");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n = rows * C;
   if (n == 0) return A3T_OK;
   if (dtype_y == A3T_BF16)
-    bn_act_fwd_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(z, mean, rstd, gamma, beta, res, (__nv_bfloat16*)y,
+    bn_act_fwd_kernel<__nv_bfloat16><<<ew_blocks(n / 4), 256, 0, st>>>(z, mean, rstd, gamma, beta, res, (__nv_bfloat16*)y,
                                                                    rows, C, act, drop_p, seed, site);
   else
-    bn_act_fwd_kernel<float><<<ew_blocks(n), 256, 0, st>>>(z, mean, rstd, gamma, beta, res, (float*)y, rows, C, act,
+    bn_act_fwd_kernel<float><<<ew_blocks(n / 4), 256, 0, st>>>(z, mean, rstd, gamma, beta, res, (float*)y, rows, C, act,
                                                            drop_p, seed, site);
   return check_launch("bn_act_fwd");
 }
@@ -586,9 +788,10 @@ extern "C" int a3t_bn_act_bwd(const float* dy, const float* z, const float* mean
   A3T_REQUIRE(dy && z && mean && rstd && gamma && beta && dz && dgamma && dbeta && partial && coef,
               "bn_act_bwd: null pointer");
   A3T_REQUIRE(drop_p == 0.f || seed, "bn_act_bwd: dropout needs a seed");
+  A3T_REQUIRE(C % 4 == 0, "bn_act_bwd: C=%d must be a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = colsum_blocks_host(rows);
-  dim3 grid((C + 255) / 256, nblk);
+  dim3 grid((C + 127) / 128, nblk);
   bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, partial, rows, C, act, drop_p, seed, site);
   int rc = check_launch("bn_bwd_partial");
   if (rc) return rc;
@@ -596,7 +799,7 @@ extern "C" int a3t_bn_act_bwd(const float* dy, const float* z, const float* mean
   rc = check_launch("bn_bwd_final");
   if (rc) return rc;
   int64_t n = rows * C;
-  bn_bwd_dz_kernel<<<ew_blocks(n), 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, coef, dz, rows, C, act, training,
+  bn_bwd_dz_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, coef, dz, rows, C, act, training,
                                                  drop_p, seed, site);
   return check_launch("bn_bwd_dz");
 }
