@@ -22,7 +22,11 @@ from . import _lib, graph
 
 class DataParallelTrainer:
     def __init__(self, model, lr: float = 1.0, warmup: float = 4000.0, model_size: Optional[float] = None,
-                 betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None, ops=None,
+                 update_fn=None):
+        """`ops` / `update_fn` exist for the CPU multi-process tests only (tests/test_dist_cpu.py passes the
+        oracle backend and a torch restatement of `a3t_adam_step` to exercise the flat-buffer exchange
+        over gloo); the product path leaves them None and requires a CUDA model."""
         self.model = model
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -30,7 +34,7 @@ class DataParallelTrainer:
         self.model_size = float(model_size if model_size is not None else model.encoder.attention_dim)
         params = [(n, p) for n, p in model.named_parameters()]
         dev = params[0][1].device
-        if dev.type != "cuda":
+        if dev.type != "cuda" and (ops is None or update_fn is None):
             raise _lib.A3TError("DataParallelTrainer needs the model on a CUDA device")
         self.device = dev
         self.names = [n for n, _ in params]
@@ -52,7 +56,8 @@ class DataParallelTrainer:
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.sq_partial = torch.zeros(1024, dtype=torch.float64, device=dev)
-        self.ops = model._backend(dev)
+        self.ops = ops if ops is not None else model._backend(dev)
+        self._update_fn = update_fn
         self.stats = self.flat_g[self.n:]
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -72,6 +77,10 @@ class DataParallelTrainer:
         self.stats[3:4].fill_(0.0)
         if self.world > 1:  # C3 (+C5/C6 piggy-backed): the single collective of the step
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        if self._update_fn is not None:  # CPU test seam
+            self._update_fn(self)
+            wc.clear()
+            return self.stats
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.call("a3t_grad_sqnorm", self.flat_g.data_ptr(), self.n, self.sq.data_ptr(), self.sq_partial.data_ptr(), st)
         _lib.call("a3t_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),

@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the frontend / vocoder side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -406,6 +407,15 @@ def main():
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     alg_flops_step = 3.0 * B * fwd_flops_per_sample(Ts, Tt)
 
+    aux = None
+    if rank == 0 and not args.no_aux:
+        # the two bandwidth-framed satellites of the path (north_star): STFT->log-mel frontend and PWG generator
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_aux
+            aux = bench_aux.measure(pwg_batch=2, peaks=peaks)
+        except Exception as e:  # reported, never hidden
+            aux = {"error": repr(e)[:200]}
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline_leg(args)
         out = {
@@ -425,7 +435,7 @@ def main():
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
-            "gpu_launches": counts["kernels"] * args.steps, "clocks": clk,
+            "gpu_launches": counts["kernels"] * args.steps, "clocks": clk, "aux": aux,
         }
         print(json.dumps(out))
     if world > 1:

@@ -102,3 +102,21 @@ def test_tc_is_what_auto_picks(cuda_lib):
                  sa_m=384, sa_k=1, sb_n=1152, sb_tap=384, sb_k=1, sc_m=1536, sc_n=1)
     y = torch.empty(1, 1152, 1536, dtype=torch.bfloat16, device="cuda")
     assert _lib.call("a3t_gemm_tc_supported", d, x.data_ptr(), pw.fwd.data_ptr(), y.data_ptr()) == 1
+
+
+@pytest.mark.parametrize("taps,C,N,S,B", [(3, 384, 1536, 1152, 2), (1, 384, 384, 1152, 3), (5, 80, 256, 200, 3)])
+def test_cta_pair_mode(bes, monkeypatch, taps, C, N, S, B):
+    """cta_group::2 (256 x N tiles on a CTA pair, opt-in through A3T_TC_CTA=2): same results as the
+    single-CTA kernel, including an odd number of M tiles (phantom second tile) and split-K wgrad."""
+    tc, simt = bes
+    monkeypatch.setenv("A3T_TC_CTA", "2")
+    x = g(B, S, C, seed=11)
+    w = g(N, C, taps, seed=12, scale=1.0 / math.sqrt(C * taps), dtype=torch.float32)
+    bias = g(N, seed=13, dtype=torch.float32)
+    res = g(B, S, N, seed=14, dtype=torch.float32)
+    pw_t, pw_s = tc.pack_weight(w), simt.pack_weight(w)
+    close(tc.conv_fwd(x, pw_t, bias, drop=(0.5, 9), residual=res, out_scale=0.5),
+          simt.conv_fwd(x, pw_s, bias, drop=(0.5, 9), residual=res, out_scale=0.5))
+    dy = g(B, S, N, seed=15)
+    close(tc.conv_dgrad(dy, pw_t, out_dtype=torch.float32), simt.conv_dgrad(dy, pw_s, out_dtype=torch.float32))
+    close(tc.conv_wgrad(dy, x, taps), simt.conv_wgrad(dy, x, taps))
