@@ -820,7 +820,8 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     astr[0] = d.sa_k; astr[1] = (int64_t)d.seq * d.sa_k; astr[2] = astr[1];
     bdims[0] = d.cin; bdims[1] = d.seq; bdims[2] = d.K / d.seq; bdims[3] = 1;
     bstr[0] = d.sb_k; bstr[1] = (int64_t)d.seq * d.sb_k; bstr[2] = bstr[1];
-    p.m_tiles_per_seq = p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.m_tiles_per_seq = 1 << 30;  // one "sequence": tile index -> row offset, also for the phantom tile of a CTA pair
     p.cblocks = ceil_div(d.seq, BLOCK_K);
     p.k_iters = (d.K / d.seq) * p.cblocks;
     nlim = d.cin;
@@ -842,7 +843,8 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     adims[3] = p.a_c3 ? d.batch1 : 1; astr[2] = p.a_c3 ? d.sa_b1 : a_row;
     bdims[2] = p.b_c2 ? d.batch2 : 1; bstr[1] = p.b_c2 ? d.sb_b2 : b_row;
     bdims[3] = p.b_c3 ? d.batch1 : 1; bstr[2] = p.b_c3 ? d.sb_b1 : b_row;
-    p.m_tiles_per_seq = p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.m_tiles = ceil_div(d.M, BLOCK_M);
+    p.m_tiles_per_seq = 1 << 30;  // one "sequence": tile index -> row offset, also for the phantom tile of a CTA pair
     p.k_iters = ceil_div(d.K, BLOCK_K);
   }
   for (int i = 0; i < 3; i++)

@@ -266,7 +266,7 @@ def run_reference(args):
 
 def cpu_baseline_leg(args):
     """Bounded CPU sample on rank 0 (reported beside the GPU number)."""
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
                         "--cpu-batch", str(args.cpu_batch), "--frames", str(args.frames), "--phones", str(args.phones)],
                        capture_output=True, text=True, timeout=900)
     for line in r.stdout.strip().splitlines()[::-1]:
@@ -287,7 +287,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--phones", type=int, default=128)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the frontend / vocoder side measurements")
@@ -439,7 +439,15 @@ def main():
         }
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL kernels captured in a CUDA graph keep the communicator busy at teardown: destroy_process_group()
+        # was observed to hang after the result line had been printed.  Release the graph, agree that every
+        # rank is done, flush, and leave without running the NCCL / graph destructors.
+        graph_obj = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
