@@ -44,6 +44,12 @@ class GemmDesc(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("w", C.c_void_p * 4), ("fwd", C.c_void_p), ("dgrad", C.c_void_p),
+                ("N", C.c_int32), ("C", C.c_int32), ("taps", C.c_int32), ("seg_rows", C.c_int32),
+                ("tile_start", C.c_int32), ("tiles_c", C.c_int32), ("_pad", C.c_int32 * 2)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -56,6 +62,8 @@ _SIGS = {
     "a3t_gemm": [C.POINTER(GemmDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "a3t_gemm_tc_supported": [C.POINTER(GemmDesc), _P, _P, _P],
     "a3t_pack_conv_weight": [_P, _I, _I, _I, _P, _P, _P],
+    "a3t_pack_conv_weights": [_P, _I, _I, _I, _P],
+    "a3t_qkv4_bias": [_P, _P, _P, _P, _P, _P, _I, _P],
     "a3t_layernorm_fwd": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _F, _I, _F, _F, _P, _U, _P],
     "a3t_layernorm_bwd_blocks": [_L],
     "a3t_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _U, _P],

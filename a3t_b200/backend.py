@@ -108,6 +108,34 @@ class CudaBackend:
         call("a3t_pack_conv_weight", _p(w3), N, Cc, taps, _p(fwd), _p(dg), _stream(w3))
         return PackedWeight(w3, N, Cc, taps, fwd, dg)
 
+    def build_pack_plan(self, entries):
+        """entries: list of (source weights stacked along N, PackedWeight with persistent bf16 packs).
+        Returns the device table `a3t_pack_conv_weights` consumes, or None when an entry cannot be batched."""
+        if self.act_dtype != torch.bfloat16 or not entries:
+            return None
+        items = (_lib.PackItem * len(entries))()
+        tile, max_taps = 0, 1
+        for i, (srcs, pw) in enumerate(entries):
+            if pw.fwd is None or pw.N % len(srcs) or (len(srcs) > 1 and (pw.N // len(srcs)) % 32) or pw.taps > 11:
+                return None
+            it = items[i]
+            for j in range(4):
+                it.w[j] = srcs[j].data_ptr() if j < len(srcs) else None
+            it.fwd, it.dgrad = pw.fwd.data_ptr(), pw.dgrad.data_ptr()
+            it.N, it.C, it.taps, it.seg_rows = pw.N, pw.C, pw.taps, pw.N // len(srcs)
+            it.tile_start, it.tiles_c = tile, (pw.C + 31) // 32
+            tile += ((pw.N + 31) // 32) * it.tiles_c
+            max_taps = max(max_taps, pw.taps)
+        table = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.device)
+        return dict(table=table, n=len(entries), tiles=tile, max_taps=max_taps, keep=entries)
+
+    def repack(self, plan):
+        call("a3t_pack_conv_weights", plan["table"].data_ptr(), plan["n"], plan["tiles"], plan["max_taps"],
+             _stream(plan["table"]))
+
+    def qkv4_bias(self, bq, bk, bv, u, v, out):
+        call("a3t_qkv4_bias", _p(bq), _p(bk), _p(bv), _p(u), _p(v), _p(out), bq.numel(), _stream(out))
+
     # ------------------------------------------------------------------ conv / linear family
     def conv_fwd(self, x, pw: PackedWeight, bias=None, *, relu=False, drop=None, residual=None, out_scale=1.0,
                  out_dtype=None):

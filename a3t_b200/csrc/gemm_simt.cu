@@ -194,6 +194,68 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
   }
 }
 
+// batched variant: block -> (item, n tile, c tile) through the items' running tile counts
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const A3tPackItem* __restrict__ items, int n_items) {
+  extern __shared__ float tile[];
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {  // last item whose tile_start <= blockIdx.x
+      int mid = (lo + hi + 1) >> 1;
+      if (items[mid].tile_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_item = lo;
+  }
+  __syncthreads();
+  const A3tPackItem it = items[s_item];
+  const int local = blockIdx.x - it.tile_start;
+  const int n0 = (local / it.tiles_c) * PK_T, c0 = (local % it.tiles_c) * PK_T;
+  const int N = it.N, C = it.C, taps = it.taps;
+  const int rowlen = PK_T * taps, ld = rowlen + 1;
+  const int seg = n0 / it.seg_rows;                  // a 32-row tile never straddles two sources
+  const float* __restrict__ w = it.w[seg];
+  const int nb = n0 - seg * it.seg_rows;             // row of the tile inside its source
+  const int seg_n = min(it.seg_rows, N - seg * it.seg_rows);
+  for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
+    int n = idx / rowlen, j = idx - n * rowlen;
+    int c = c0 + j / taps;
+    float v = 0.f;
+    if (nb + n < seg_n && c < C) v = w[((int64_t)(nb + n) * C + c0) * taps + j];
+    tile[n * ld + j] = v;
+  }
+  __syncthreads();
+  __nv_bfloat16* fwd = (__nv_bfloat16*)it.fwd;
+  __nv_bfloat16* dg = (__nv_bfloat16*)it.dgrad;
+  if (fwd) {
+    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
+      int cc = idx % PK_T, r = idx / PK_T;
+      int tap = r % taps, n = r / taps;
+      if (n0 + n < N && nb + n < seg_n && c0 + cc < C)
+        fwd[(int64_t)(n0 + n) * taps * C + (int64_t)tap * C + c0 + cc] = __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+    }
+  }
+  if (dg) {
+    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
+      int n = idx % PK_T, r = idx / PK_T;
+      int tap = r % taps, cc = r / taps;
+      if (n0 + n < N && nb + n < seg_n && c0 + cc < C)
+        dg[(int64_t)(c0 + cc) * taps * N + (int64_t)(taps - 1 - tap) * N + n0 + n] =
+            __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+    }
+  }
+}
+
+__global__ void qkv4_bias_kernel(const float* __restrict__ bq, const float* __restrict__ bk, const float* __restrict__ bv,
+                                 const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ out,
+                                 int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  out[i] = bq[i] + u[i];
+  out[D + i] = bq[i] + v[i];
+  out[2 * D + i] = bk[i];
+  out[3 * D + i] = bv[i];
+}
+
 }  // namespace a3t
 
 extern "C" const char* a3t_last_error(void) { return a3t::g_err; }
@@ -207,4 +269,19 @@ extern "C" int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void
   a3t::pack_conv_weight_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, N, C, taps, (__nv_bfloat16*)fwd,
                                                                          (__nv_bfloat16*)dg);
   return a3t::check_launch("pack_conv_weight");
+}
+
+extern "C" int a3t_pack_conv_weights(const A3tPackItem* items, int n_items, int total_tiles, int max_taps, void* stream) {
+  A3T_REQUIRE(items && n_items > 0 && total_tiles > 0, "pack_conv_weights: bad args");
+  A3T_REQUIRE(max_taps >= 1 && max_taps <= 11, "pack_conv_weights: max_taps=%d out of range (1..11)", max_taps);
+  size_t smem = (size_t)a3t::PK_T * (a3t::PK_T * max_taps + 1) * sizeof(float);
+  a3t::pack_conv_weights_kernel<<<total_tiles, 256, smem, (cudaStream_t)stream>>>(items, n_items);
+  return a3t::check_launch("pack_conv_weights");
+}
+
+extern "C" int a3t_qkv4_bias(const float* bq, const float* bk, const float* bv, const float* u, const float* v,
+                             float* out, int D, void* stream) {
+  A3T_REQUIRE(bq && bk && bv && u && v && out && D > 0, "qkv4_bias: bad args");
+  a3t::qkv4_bias_kernel<<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bq, bk, bv, u, v, out, D);
+  return a3t::check_launch("qkv4_bias");
 }

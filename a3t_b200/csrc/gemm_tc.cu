@@ -413,6 +413,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(full_bar(s), stage_bytes);
             for (int j = 0; j < a_boxes; j++)
               tma_load_4d(sa + j * (BLOCK_K * 128), &tmA, full_bar(s), ai + 64 * j, ao, a2, a3);
+            if (p.dbg == 4 && !p.b_mn) {  // experiment: the same B bytes as 4 requests instead of 1
+              for (int j = 0; j < 4; j++)
+                tma_load_4d(sb + j * (b_rows / 4) * 128, &tmB, full_bar(s), bi, bo + j * (b_rows / 4), b2, b3);
+            } else
             for (int j = 0; j < b_boxes; j++)
               tma_load_4d(sb + j * (BLOCK_K * 128), &tmB, full_bar(s), bi + 64 * j, bo, b2, b3);
           }
@@ -971,6 +975,10 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
   }
   if (const char* e = getenv("A3T_TC_DBGMODE")) p.dbg = atoi(e);
+  if (p.dbg == 4 && !p.b_mn && !cta2 && (b_rows % 32) == 0) {  // re-encode B with quarter-height boxes
+    bbox[1] = b_rows / 4;
+    if (!encode_map(&tmB, B, bdims, bstr, bbox)) return A3T_ERR_UNSUPPORTED;
+  } else if (p.dbg == 4) p.dbg = 0;
   if (getenv("A3T_TC_DEBUG"))
     fprintf(stderr, "gemm_tc: M=%d N=%d K=%d mode=%d cta2=%d bn=%d splits=%d stages=%d work=%d epi=%d\n", d.M, d.N, d.K,
             d.mode, (int)cta2, p.block_n, p.splits, p.stages, p.num_work, epi);

@@ -128,15 +128,35 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const double bc2 = 1.0 - pow((double)beta2, step);
   const float step_size = (float)(lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  for (int64_t i = tid; i < n4; i += stride) {  // 16-byte accesses: 28 B of traffic per parameter
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    float ge[4] = {g4.x, g4.y, g4.z, g4.w}, me[4] = {m4.x, m4.y, m4.z, m4.w}, ve[4] = {v4.x, v4.y, v4.z, v4.w};
+    float pe[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      float gi = ge[e] * gs;
+      me[e] = me[e] * beta1 + gi * (1.f - beta1);
+      ve[e] = ve[e] * beta2 + gi * gi * (1.f - beta2);
+      float dn = sqrtf(ve[e]) * inv_sqrt_bc2 + eps;
+      pe[e] = pe[e] - step_size * (me[e] / dn);
+    }
+    reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+    reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
     float gi = g[i] * gs;
     float mi = m[i] * beta1 + gi * (1.f - beta1);
     float vi = v[i] * beta2 + gi * gi * (1.f - beta2);
     m[i] = mi;
     v[i] = vi;
-    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    float dn = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - step_size * (mi / dn);
   }
 }
 __global__ void step_advance_kernel(const double* __restrict__ sq, int64_t* __restrict__ step_p, float grad_scale,

@@ -59,6 +59,7 @@ class DataParallelTrainer:
         self.ops = ops if ops is not None else model._backend(dev)
         self._update_fn = update_fn
         self.stats = self.flat_g[self.n:]
+        self._plan, self._plan_tried, self._qkv4 = None, False, []
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """One optimizer step on this rank's shard of the global batch.  Returns the device tensor
@@ -87,6 +88,34 @@ class DataParallelTrainer:
                   self.flat_v.data_ptr(), self.n, self.sq.data_ptr(), self.step_count.data_ptr(), self.lr,
                   self.model_size, self.warmup, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
                   self.stats[2:3].data_ptr(), st)
-        wc.clear()  # parameters changed under the packed bf16 copies
+        self._refresh_packed_weights(P, wc)  # parameters changed under the packed bf16 copies
         ops.advance_seed()
         return self.stats
+
+    def _refresh_packed_weights(self, P, wc):
+        """The bf16 GEMM operand copies of every weight are rewritten IN PLACE by one batched kernel (the
+        parameters live at fixed addresses inside `flat_p`), so the weight cache stays valid and the next
+        step launches no per-weight packing kernels.  Falls back to dropping the cache (lazy re-pack)."""
+        ops = self.ops
+        if not self._plan_tried:
+            self._plan_tried = True
+            entries, qkv4 = [], []
+            for key, (_, val) in wc._c.items():
+                if key.endswith(".qkv4"):
+                    a = key[:-len(".qkv4")]
+                    pw, b4 = val
+                    wq, wk, wv = (P[f"{a}.linear_{n}.weight"] for n in "qkv")
+                    entries.append(([wq, wq, wk, wv], pw))
+                    qkv4.append((P[f"{a}.linear_q.bias"], P[f"{a}.linear_k.bias"], P[f"{a}.linear_v.bias"],
+                                 P[f"{a}.pos_bias_u"], P[f"{a}.pos_bias_v"], b4))
+                else:
+                    entries.append(([val.w], val))
+            plan = ops.build_pack_plan(entries) if hasattr(ops, "build_pack_plan") else None
+            if plan is not None:
+                self._plan, self._qkv4 = plan, qkv4
+        if self._plan is None:
+            wc.clear()
+            return
+        ops.repack(self._plan)
+        for bq, bk, bv, u, v, b4 in self._qkv4:
+            ops.qkv4_bias(bq, bk, bv, u, v, b4)

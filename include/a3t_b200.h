@@ -99,6 +99,25 @@ int a3t_gemm_tc_supported(const A3tGemmDesc* d, const void* A, const void* B, vo
 int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void* fwd_bf16, void* dgrad_bf16,
                          void* stream);
 
+/* Batched form of a3t_pack_conv_weight: ONE launch repacks every GEMM weight of the model after an optimizer
+ * step.  `items` is a DEVICE array; an item may stack up to 4 source weights along N (the fused
+ * [q+u | q+v | k | v] projection packs [Wq, Wq, Wk, Wv] without materialising the concatenation; seg_rows rows
+ * per source, a multiple of 32 when more than one source is used).  tile_start = running count of 32x32 tiles
+ * (ceil(N/32) * ceil(C/32) per item); total_tiles = the sum; max_taps = largest taps of any item (<= 11). */
+typedef struct A3tPackItem {
+  const float* w[4];
+  void* fwd;    /* bf16 (N, taps*C) or NULL */
+  void* dgrad;  /* bf16 (C, taps*N) or NULL */
+  int32_t N, C, taps, seg_rows;
+  int32_t tile_start, tiles_c;
+  int32_t _pad[2];
+} A3tPackItem;
+int a3t_pack_conv_weights(const A3tPackItem* items, int n_items, int total_tiles, int max_taps, void* stream);
+/* bias of the fused projection: out = [bq + u | bq + v | bk | bv]  (each D floats; u, v = pos_bias_{u,v} flattened,
+ * transformer/attention.py:190-202 adds them to q before the two score products) */
+int a3t_qkv4_bias(const float* bq, const float* bk, const float* bv, const float* u, const float* v, float* out,
+                  int D, void* stream);
+
 /* LayerNorm over the last dim (transformer/layer_norm.py:23 eps 1e-12; conformer/encoder.py:404
  * eps 1e-5 followed by ReLU, embedding.py:168 x*sqrt(D), dropout).
  * y = dropout( relu?(LN(x)) * out_scale ); mean/rstd (rows) are saved for the backward. */
