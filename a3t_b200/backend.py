@@ -292,10 +292,12 @@ class CudaBackend:
         Bn, S, D4 = qkv4.shape
         D = D4 // 4
         dk = D // H
-        ac = torch.empty(Bn, H, S, S, dtype=torch.float32, device=qkv4.device)
-        bd = torch.empty(Bn, H, S, S, dtype=torch.float32, device=qkv4.device)
+        # score tensors in the activation dtype: fp32 in the parity mode; bf16 in the tensor-core mode, where P
+        # itself is stored in bf16 (halves the bytes the memory-bound softmax kernel reads)
+        ac = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
+        bd = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
         dt = _dt(qkv4)
-        common = dict(batch1=Bn, batch2=H, dtype_a=dt, dtype_b=dt, dtype_c=A3T_F32, sa_m=D4, sa_k=1, sa_b1=S * D4,
+        common = dict(batch1=Bn, batch2=H, dtype_a=dt, dtype_b=dt, dtype_c=_dt(ac), sa_m=D4, sa_k=1, sa_b1=S * D4,
                       sa_b2=dk, sc_m=S, sc_n=1, sc_b1=H * S * S, sc_b2=S * S)
         d = self._desc(S, S, dk, sb_n=D4, sb_k=1, sb_b1=S * D4, sb_b2=dk, **common)
         self._gemm(d, qkv4, qkv4, ac, a_off=0, b_off=2 * D)
@@ -308,7 +310,7 @@ class CudaBackend:
         P = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=ac.device)
         p, seed, site = self._drop(drop)
         Pd = torch.empty_like(P) if p > 0 else P
-        call("a3t_relpos_softmax_fwd", _p(ac), _p(bd_raw), _p(_u8(keymask)), _p(P), _p(Pd), _dt(P), Bn, H, S, scale, p,
+        call("a3t_relpos_softmax_fwd", _p(ac), _p(bd_raw), _dt(ac), _p(_u8(keymask)), _p(P), _p(Pd), _dt(P), Bn, H, S, scale, p,
              seed, site, _stream(ac))
         return P, Pd
 
@@ -328,8 +330,8 @@ class CudaBackend:
         Bn, S, D4 = qkv4.shape
         D = D4 // 4
         dk = D // H
-        dPd = torch.empty(Bn, H, S, S, dtype=torch.float32, device=qkv4.device)
-        d = self._desc(S, S, dk, batch1=Bn, batch2=H, dtype_a=_dt(dctx), dtype_b=_dt(qkv4), dtype_c=A3T_F32, sa_m=D,
+        dPd = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
+        d = self._desc(S, S, dk, batch1=Bn, batch2=H, dtype_a=_dt(dctx), dtype_b=_dt(qkv4), dtype_c=_dt(dPd), sa_m=D,
                        sa_k=1, sa_b1=S * D, sa_b2=dk, sb_n=D4, sb_k=1, sb_b1=S * D4, sb_b2=dk, sc_m=S, sc_n=1,
                        sc_b1=H * S * S, sc_b2=S * S)
         self._gemm(d, dctx, qkv4, dPd, b_off=3 * D)
@@ -344,7 +346,7 @@ class CudaBackend:
         dS = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=P.device)
         dBD = torch.empty_like(dS)
         p, seed, site = self._drop(drop)
-        call("a3t_relpos_softmax_bwd", _p(dPd), _p(P), _dt(P), _p(dS), _p(dBD), _dt(dS), Bn, H, S, scale, p, seed, site,
+        call("a3t_relpos_softmax_bwd", _p(dPd), _dt(dPd), _p(P), _dt(P), _p(dS), _p(dBD), _dt(dS), Bn, H, S, scale, p, seed, site,
              _stream(P))
         return dS, dBD
 

@@ -10,16 +10,16 @@ constexpr int SM_WARPS = 4;
 
 // rel_shift gather: padded view (S, S+1) with a zero first column, reinterpreted as (S+1, S),
 // first row dropped.  shifted[i,j] = padded_flat[(i+1)*S + j].
-__device__ __forceinline__ float bd_shifted(const float* __restrict__ bd, int S, int i, int j) {
+__device__ __forceinline__ float bd_shifted(const void* __restrict__ bd, int dt, int64_t mat, int S, int i, int j) {
   int64_t f = (int64_t)(i + 1) * S + j;
   int r = (int)(f / (S + 1));
   int c = (int)(f - (int64_t)r * (S + 1));
-  return c == 0 ? 0.f : bd[(int64_t)r * S + (c - 1)];
+  return c == 0 ? 0.f : load_as_f32(bd, dt, mat + (int64_t)r * S + (c - 1));
 }
 
 template <typename TP>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
-    const float* __restrict__ ac, const float* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
+    const void* __restrict__ ac, const void* __restrict__ bd_raw, int dt_in, const uint8_t* __restrict__ keymask,
     TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
   extern __shared__ float sm[];
@@ -31,12 +31,10 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
     const int i = (int)(r % S);
     const int64_t bh = r / S;
     const int b = (int)(bh / H);
-    const float* acr = ac + r * S;
-    const float* bdm = bd_raw + bh * (int64_t)S * S;
     const uint8_t* km = keymask + (int64_t)b * S;
     float mx = -FLT_MAX;
     for (int j = lane; j < S; j += 32) {
-      float s = (acr[j] + bd_shifted(bdm, S, i, j)) * scale;
+      float s = (load_as_f32(ac, dt_in, r * S + j) + bd_shifted(bd_raw, dt_in, bh * (int64_t)S * S, S, i, j)) * scale;
       if (!km[j]) s = -FLT_MAX;  // finfo(float32).min
       row[j] = s;
       mx = fmaxf(mx, s);
@@ -63,7 +61,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
 // dS[i,j] = P * (dPu - sum_j dPu*P) * scale ; dPu = dPd*keep/(1-p)
 template <typename TP, typename TO>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
-    const float* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, float scale,
+    const void* __restrict__ dPd, int dt_in, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, float scale,
     float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,7 +70,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
   for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
     float dot = 0.f;
     for (int j = lane; j < S; j += 32) {
-      float g = dPd[r * S + j];
+      float g = load_as_f32(dPd, dt_in, r * S + j);
       if (dr.on) g = drop_keep(dr, (unsigned long long)(r * S + j)) ? g * dr.inv_keep : 0.f;
       row[j] = g;
       dot += g * to_f32<TP>(P[r * S + j]);
@@ -135,9 +133,9 @@ __device__ __forceinline__ void load_p4<__nv_bfloat16>(const __nv_bfloat16* p, f
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-template <typename TP>
+template <typename TP, typename TI>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
-    const float* __restrict__ ac, const float* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
+    const TI* __restrict__ ac, const TI* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
     TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
   extern __shared__ float sm[];
@@ -149,23 +147,23 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
     const int i = (int)(r % S);
     const int64_t bh = r / S;
     const int b = (int)(bh / H);
-    const float* acr = ac + r * S;
-    const float* bd0 = bd_raw + (bh * S + i) * (int64_t)S + (S - 1 - i);   // + j       for j <= i
-    const float* bd1 = bd_raw + (bh * S + i + 1) * (int64_t)S - (i + 2);   // + j       for j >= i+2
+    const TI* acr = ac + r * S;
+    const TI* bd0 = bd_raw + (bh * S + i) * (int64_t)S + (S - 1 - i);   // + j       for j <= i
+    const TI* bd1 = bd_raw + (bh * S + i + 1) * (int64_t)S - (i + 2);   // + j       for j >= i+2
     const uint8_t* km = keymask + (int64_t)b * S;
     float mx = -FLT_MAX;
     for (int j = lane * 4; j < S; j += 128) {
-      const float4 a4 = *reinterpret_cast<const float4*>(acr + j);
+      float a[4];
+      load_p4<TI>(acr + j, a);
       const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
       const unsigned char kk[4] = {k4.x, k4.y, k4.z, k4.w};
       float sv[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const int jj = j + e;
         float bd = 0.f;
-        if (jj <= i) bd = bd0[jj];
-        else if (jj >= i + 2) bd = bd1[jj];
+        if (jj <= i) bd = to_f32<TI>(bd0[jj]);
+        else if (jj >= i + 2) bd = to_f32<TI>(bd1[jj]);
         float v = (a[e] + bd) * scale;
         if (!kk[e]) v = -FLT_MAX;  // finfo(float32).min
         sv[e] = v;
@@ -205,9 +203,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
 // dS = P * (dPu - sum_j dPu*P) * scale, and dBD_raw = inverse rel_shift of dS written by the same warp:
 //   row i of dS feeds dBD[i, S-1-i+j] (j <= i) and dBD[i+1, j-i-2] (j >= i+2); row 0 of dBD is zero
 //   except its last element.  Every dBD element is written exactly once.
-template <typename TP, typename TO>
+template <typename TP, typename TO, typename TI>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
-    const float* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nrows,
+    const TI* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nrows,
     int S, float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -217,8 +215,8 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
     const int i = (int)(r % S);
     float dot = 0.f;
     for (int j = lane * 4; j < S; j += 128) {
-      const float4 g4 = *reinterpret_cast<const float4*>(dPd + r * S + j);
-      float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      float g[4];
+      load_p4<TI>(dPd + r * S + j, g);
       float pv[4];
       load_p4<TP>(P + r * S + j, pv);
       if (dr.on) {
@@ -258,12 +256,13 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
 
 using namespace a3t;
 
-extern "C" int a3t_relpos_softmax_fwd(const float* ac, const float* bd_raw, const uint8_t* keymask, void* P, void* Pd,
-                                      int dtype_p, int B, int H, int S, float scale, float drop_p,
+extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dtype_in, const uint8_t* keymask, void* P,
+                                      void* Pd, int dtype_p, int B, int H, int S, float scale, float drop_p,
                                       const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(ac && bd_raw && keymask && P && Pd, "relpos_softmax_fwd: null pointer");
   A3T_REQUIRE(drop_p == 0.f || (seed && Pd != P), "relpos_softmax_fwd: dropout needs a seed and a separate Pd");
   A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_fwd: S=%d out of range", S);
+  A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_fwd: bad input dtype");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t nrows = (int64_t)B * H * S;
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
@@ -271,44 +270,49 @@ extern "C" int a3t_relpos_softmax_fwd(const float* ac, const float* bd_raw, cons
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
   const bool v4 = (S % 4) == 0 && ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
   if (v4 && smem <= 48 * 1024) {
-    if (dtype_p == A3T_BF16)
-      relpos_softmax_fwd_v4_kernel<__nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
-          ac, bd_raw, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
-    else
-      relpos_softmax_fwd_v4_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, keymask, (float*)P,
-                                                                              (float*)Pd, B, H, S, scale, drop_p, seed, site);
+#define A3T_SM_FWD(TPT, TIT)                                                                              \
+  relpos_softmax_fwd_v4_kernel<TPT, TIT><<<blocks, SM_WARPS * 32, smem, st>>>(                            \
+      (const TIT*)ac, (const TIT*)bd_raw, keymask, (TPT*)P, (TPT*)Pd, B, H, S, scale, drop_p, seed, site)
+    if (dtype_p == A3T_BF16 && dtype_in == A3T_BF16) A3T_SM_FWD(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype_p == A3T_BF16) A3T_SM_FWD(__nv_bfloat16, float);
+    else if (dtype_in == A3T_BF16) A3T_SM_FWD(float, __nv_bfloat16);
+    else A3T_SM_FWD(float, float);
     return check_launch("relpos_softmax_fwd");
   }
   if (dtype_p == A3T_BF16) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(relpos_softmax_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     relpos_softmax_fwd_kernel<__nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
-        ac, bd_raw, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
+        ac, bd_raw, dtype_in, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(relpos_softmax_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    relpos_softmax_fwd_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, keymask, (float*)P, (float*)Pd, B,
-                                                                         H, S, scale, drop_p, seed, site);
+    relpos_softmax_fwd_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, dtype_in, keymask, (float*)P,
+                                                                         (float*)Pd, B, H, S, scale, drop_p, seed, site);
   }
   return check_launch("relpos_softmax_fwd");
 }
 
 template <typename TP, typename TO>
-static int softmax_bwd_launch(const float* dPd, const void* P, void* dS, void* dBD, int B, int H, int S, float scale,
-                              float drop_p, const unsigned long long* seed, uint32_t site, cudaStream_t st) {
+static int softmax_bwd_launch(const void* dPd, int dtype_in, const void* P, void* dS, void* dBD, int B, int H, int S,
+                              float scale, float drop_p, const unsigned long long* seed, uint32_t site, cudaStream_t st) {
   int64_t nrows = (int64_t)B * H * S;
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
   if ((S % 4) == 0 && smem <= 48 * 1024 && ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0)) {
-    relpos_softmax_bwd_v4_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows,
-                                                                             S, scale, drop_p, seed, site);
+    if (dtype_in == A3T_BF16)
+      relpos_softmax_bwd_v4_kernel<TP, TO, __nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
+          (const __nv_bfloat16*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, scale, drop_p, seed, site);
+    else
+      relpos_softmax_bwd_v4_kernel<TP, TO, float><<<blocks, SM_WARPS * 32, smem, st>>>(
+          (const float*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, scale, drop_p, seed, site);
     return check_launch("relpos_softmax_bwd");
   }
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(relpos_softmax_bwd_kernel<TP, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, (const TP*)P, (TO*)dS, nrows, S, scale,
-                                                                        drop_p, seed, site);
+  relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, dtype_in, (const TP*)P, (TO*)dS, nrows, S,
+                                                                        scale, drop_p, seed, site);
   int rc = check_launch("relpos_softmax_bwd");
   if (rc) return rc;
   int64_t n = nrows * S;
@@ -318,19 +322,20 @@ static int softmax_bwd_launch(const float* dPd, const void* P, void* dS, void* d
   return check_launch("relshift_bwd");
 }
 
-extern "C" int a3t_relpos_softmax_bwd(const float* dPd, const void* P, int dtype_p, void* dS, void* dBD, int dtype_o,
-                                      int B, int H, int S, float scale, float drop_p, const unsigned long long* seed,
-                                      uint32_t site, void* stream) {
+extern "C" int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void* P, int dtype_p, void* dS, void* dBD,
+                                      int dtype_o, int B, int H, int S, float scale, float drop_p,
+                                      const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(dPd && P && dS && dBD, "relpos_softmax_bwd: null pointer");
   A3T_REQUIRE(drop_p == 0.f || seed, "relpos_softmax_bwd: dropout needs a seed");
   A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_bwd: S=%d out of range", S);
+  A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_bwd: bad input dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_p == A3T_BF16 && dtype_o == A3T_BF16)
-    return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
   if (dtype_p == A3T_F32 && dtype_o == A3T_F32)
-    return softmax_bwd_launch<float, float>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<float, float>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
   if (dtype_p == A3T_BF16 && dtype_o == A3T_F32)
-    return softmax_bwd_launch<__nv_bfloat16, float>(dPd, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<__nv_bfloat16, float>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
   set_error("relpos_softmax_bwd: unsupported dtype combination");
   return A3T_ERR_UNSUPPORTED;
 }

@@ -173,13 +173,14 @@ int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, const int64_t*
  * scale, :79-86 finfo.min fill / softmax / zero fill, :88 dropout).
  *   s[i,j] = (AC[i,j] + BDraw_shifted[i,j]) * scale ; key j invalid -> finfo(f32).min
  *   P = softmax_j(s), zeroed at invalid keys;  Pd = dropout(P)   (Pd may alias P when p == 0)
- * AC/BD fp32 (B,H,S,S); keymask (B,S) uint8, 1 = valid; P, Pd dtype_p. */
-int a3t_relpos_softmax_fwd(const float* ac, const float* bd_raw, const uint8_t* keymask, void* P,
+ * AC/BD (B,H,S,S) of dtype_in (fp32 in the parity mode, bf16 in the tensor-core mode: same rounding as P);
+ * keymask (B,S) uint8, 1 = valid; P, Pd dtype_p. */
+int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dtype_in, const uint8_t* keymask, void* P,
                            void* Pd, int dtype_p, int B, int H, int S, float scale, float drop_p,
                            const unsigned long long* seed, uint32_t site, void* stream);
 /* dS = P * (dPu - sum_j dPu*P) * scale with dPu = dPd*keep/(1-p);  dBD_raw = inverse rel_shift of
- * dS.  dPd fp32; dS, dBD dtype_o (B,H,S,S). */
-int a3t_relpos_softmax_bwd(const float* dPd, const void* P, int dtype_p, void* dS, void* dBD,
+ * dS.  dPd dtype_in; dS, dBD dtype_o (B,H,S,S). */
+int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void* P, int dtype_p, void* dS, void* dBD,
                            int dtype_o, int B, int H, int S, float scale, float drop_p,
                            const unsigned long long* seed, uint32_t site, void* stream);
 

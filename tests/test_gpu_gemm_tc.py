@@ -76,13 +76,13 @@ def test_attention_contractions_tc(bes, B, H, S, dk):
     qkv4, p = g(B, S, 4 * D, seed=1, scale=0.5), g(S, D, seed=2, scale=0.5)
     ac_t, bd_t = tc.attn_scores_fwd(qkv4, p, H)
     ac_s, bd_s = simt.attn_scores_fwd(qkv4, p, H)
-    close(ac_t, ac_s)
-    close(bd_t, bd_s)
+    close(ac_t, ac_s, tol=1e-2)  # bf16 score tensors: one ulp of the largest score
+    close(bd_t, bd_s, tol=1e-2)
     Pd = torch.softmax(g(B, H, S, S, seed=3, dtype=torch.float32), -1).to(torch.bfloat16)
     close(tc.attn_pv_fwd(Pd, qkv4, H), simt.attn_pv_fwd(Pd, qkv4, H), tol=1e-2)
     dctx = g(B, S, D, seed=4)
     dq_t, dq_s = torch.zeros_like(qkv4), torch.zeros_like(qkv4)
-    close(tc.attn_pv_bwd(dctx, Pd, qkv4, H, dq_t), simt.attn_pv_bwd(dctx, Pd, qkv4, H, dq_s))
+    close(tc.attn_pv_bwd(dctx, Pd, qkv4, H, dq_t), simt.attn_pv_bwd(dctx, Pd, qkv4, H, dq_s), tol=1e-2)
     dS, dBD = g(B, H, S, S, seed=5, scale=0.1), g(B, H, S, S, seed=6, scale=0.1)
     dp_t = tc.attn_scores_bwd(dS, dBD, qkv4, p, H, dq_t)
     dp_s = simt.attn_scores_bwd(dS, dBD, qkv4, p, H, dq_s)
