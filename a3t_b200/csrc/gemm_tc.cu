@@ -61,7 +61,7 @@ struct Params {
   int num_work;         // m_tiles * n_tiles * batch * splits
   int a_c2, a_c3, b_c2, b_c3;  // 0 when that batch coordinate is pinned (stride 0 / size 1)
   int vec_c, vec_r, vec_m;     // 16-byte vector access allowed for C / residual / mask
-  int dbg;                     // tuning experiments: 1 = no loads, MMAs free-run; 2 = loads run, MMAs do not wait; 3 = loads only (timing only, garbage results)
+  int dbg;                     // tuning experiments: 1 = no loads, MMAs free-run; 2 = loads run, MMAs do not wait; 3 = loads only; 5 = loads only, no epilogue; 6 = no epilogue (timing only, garbage results)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -143,6 +143,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"((uint16_t)3)
       : "memory");
+}
+// one lane of a converged warp; unlike `lane == 0` the compiler knows a single thread runs the guarded code,
+// so tcgen05 / TMA operands go to uniform registers without a per-instruction broadcast loop
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -373,84 +384,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const A3tGemmDesc& d = p.d;
 
+  const int dbg = p.dbg;
   if (warp == PRODUCER_WARP) {
     // ===================================== TMA producer =====================================
-    if (lane == 0 && p.dbg != 1) {
+    // The K loop is one thread issuing dependent instructions: it is kept to a barrier wait, the TMA
+    // instructions and a handful of adds.  Every tensor-map coordinate is linear in a two-level counter
+    // (inner j < cblocks, outer o): CONV (j = channel block, o = tap), WGRAD (j = row block inside the
+    // sequence, o = sequence), PLAIN (j = K block, never wraps) -- no division inside the loop.
+    if (elect_one() && dbg != 1) {
       int s = 0;
       uint32_t ph = 0;
       const int a_boxes = p.a_mn ? BLOCK_M / 64 : 1;
       const int b_boxes = p.b_mn ? b_rows / 64 : 1;
       const int b_off = (int)rank * b_rows;  // this CTA's slice of the B tile along N
+      // coordinate order: {a inner, a outer, a dim2, a dim3, b inner, b outer, b dim2, b dim3}
+      int dj[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int inner = p.k_iters;
+      if (d.mode == A3T_GEMM_CONV) {
+        inner = p.cblocks;
+        dj[0] = BLOCK_K; dj[4] = BLOCK_K;
+        dw[0] = -p.cblocks * BLOCK_K; dw[1] = 1; dw[4] = d.cin - p.cblocks * BLOCK_K;
+      } else if (d.mode == A3T_GEMM_WGRAD) {
+        inner = p.cblocks;
+        dj[1] = BLOCK_K; dj[5] = BLOCK_K;
+        dw[1] = -p.cblocks * BLOCK_K; dw[2] = 1; dw[5] = -p.cblocks * BLOCK_K; dw[6] = 1;
+      } else {
+        dj[p.a_mn ? 1 : 0] = BLOCK_K;
+        dj[p.b_mn ? 5 : 4] = BLOCK_K;
+      }
       for (int w = group; w < p.num_work; w += ngroups) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
+        int o0 = 0, j = t.k_begin;
+        if (inner != p.k_iters) { o0 = t.k_begin / inner; j = t.k_begin - o0 * inner; }
+        int c[8];
+        if (d.mode == A3T_GEMM_CONV) {
+          c[0] = 0; c[1] = t.m0 - d.pad; c[2] = t.seq_idx; c[3] = 0;
+          c[4] = 0; c[5] = t.n0 + b_off; c[6] = 0; c[7] = 0;
+        } else if (d.mode == A3T_GEMM_WGRAD) {
+          c[0] = t.m0; c[1] = 0; c[2] = 0; c[3] = 0;
+          c[4] = t.n0 + b_off; c[5] = t.tap_n - d.pad; c[6] = 0; c[7] = 0;
+        } else {
+          c[0] = p.a_mn ? t.m0 : 0; c[1] = p.a_mn ? 0 : t.m0; c[2] = t.b2 * p.a_c2; c[3] = t.b1 * p.a_c3;
+          c[4] = p.b_mn ? t.n0 + b_off : 0; c[5] = p.b_mn ? 0 : t.n0 + b_off; c[6] = t.b2 * p.b_c2; c[7] = t.b1 * p.b_c3;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[i] += j * dj[i] + o0 * (dw[i] + inner * dj[i]);
         for (int kit = t.k_begin; kit < t.k_end; kit++) {
-          int ai, ao, a2, a3, bi, bo, b2, b3;  // (inner, outer, dim2, dim3) coordinates
-          if (d.mode == A3T_GEMM_CONV) {
-            int tap = kit / p.cblocks, c0 = (kit - tap * p.cblocks) * BLOCK_K;
-            ai = c0; ao = t.m0 + tap - d.pad; a2 = t.seq_idx; a3 = 0;
-            bi = tap * d.cin + c0; bo = t.n0 + b_off; b2 = 0; b3 = 0;
-          } else if (d.mode == A3T_GEMM_WGRAD) {
-            int sq = kit / p.cblocks, s0 = (kit - sq * p.cblocks) * BLOCK_K;
-            ai = t.m0; ao = s0; a2 = sq; a3 = 0;
-            bi = t.n0 + b_off; bo = s0 + t.tap_n - d.pad; b2 = sq; b3 = 0;
-          } else {
-            int k0 = kit * BLOCK_K;
-            if (p.a_mn) { ai = t.m0; ao = k0; } else { ai = k0; ao = t.m0; }
-            if (p.b_mn) { bi = t.n0 + b_off; bo = k0; } else { bi = k0; bo = t.n0 + b_off; }
-            a2 = t.b2 * p.a_c2; a3 = t.b1 * p.a_c3;
-            b2 = t.b2 * p.b_c2; b3 = t.b1 * p.b_c3;
-          }
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * stage_bytes, sb = sa + A_STAGE_BYTES;
+          const uint32_t fb = full_bar(s);
           if constexpr (CTA2) {
             // one transaction barrier (the leader's) collects the bytes of both CTAs
-            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * stage_bytes);
-            for (int j = 0; j < a_boxes; j++)
-              tma_load_4d_2sm(sa + j * (BLOCK_K * 128), &tmA, full_bar(s), ai + 64 * j, ao, a2, a3);
-            for (int j = 0; j < b_boxes; j++)
-              tma_load_4d_2sm(sb + j * (BLOCK_K * 128), &tmB, full_bar(s), bi + 64 * j, bo, b2, b3);
+            if (rank == 0) mbar_expect_tx(fb, 2 * stage_bytes);
+            for (int q = 0; q < a_boxes; q++)
+              tma_load_4d_2sm(sa + q * (BLOCK_K * 128), &tmA, fb, c[0] + 64 * q, c[1], c[2], c[3]);
+            for (int q = 0; q < b_boxes; q++)
+              tma_load_4d_2sm(sb + q * (BLOCK_K * 128), &tmB, fb, c[4] + 64 * q, c[5], c[6], c[7]);
           } else {
-            mbar_expect_tx(full_bar(s), stage_bytes);
-            for (int j = 0; j < a_boxes; j++)
-              tma_load_4d(sa + j * (BLOCK_K * 128), &tmA, full_bar(s), ai + 64 * j, ao, a2, a3);
-            if (p.dbg == 4 && !p.b_mn) {  // experiment: the same B bytes as 4 requests instead of 1
-              for (int j = 0; j < 4; j++)
-                tma_load_4d(sb + j * (b_rows / 4) * 128, &tmB, full_bar(s), bi, bo + j * (b_rows / 4), b2, b3);
-            } else
-            for (int j = 0; j < b_boxes; j++)
-              tma_load_4d(sb + j * (BLOCK_K * 128), &tmB, full_bar(s), bi + 64 * j, bo, b2, b3);
+            mbar_expect_tx(fb, stage_bytes);
+            for (int q = 0; q < a_boxes; q++)
+              tma_load_4d(sa + q * (BLOCK_K * 128), &tmA, fb, c[0] + 64 * q, c[1], c[2], c[3]);
+            for (int q = 0; q < b_boxes; q++)
+              tma_load_4d(sb + q * (BLOCK_K * 128), &tmB, fb, c[4] + 64 * q, c[5], c[6], c[7]);
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
+#pragma unroll
+          for (int i = 0; i < 8; i++) c[i] += dj[i];
+          if (++j == inner) {
+            j = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) c[i] += dw[i];
+          }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0 && rank == 0) {  // pair mode: only the leader CTA issues MMAs (they span both SMs)
+    if (elect_one() && rank == 0) {  // pair mode: only the leader CTA issues MMAs (they span both SMs)
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       // per-instruction K advance inside a stage: K-major = 32 B along the swizzled row,
-      // MN-major = 16 k-rows of 128 B
-      const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
-      const uint32_t b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
-      const uint32_t a_lbo = p.a_mn ? BLOCK_K * 128 : 16;
-      const uint32_t b_lbo = p.b_mn ? BLOCK_K * 128 : 16;
+      // MN-major = 16 k-rows of 128 B.  Descriptors differ only in the 14-bit start-address field
+      // (shared memory < 256 KB, so adding byte offsets >> 4 to the low word cannot carry out of it).
+      const uint32_t a_kstep = (p.a_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t b_kstep = (p.b_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint64_t adesc0 = make_smem_desc(smem_base, p.a_mn ? BLOCK_K * 128 : 16);
+      const uint64_t bdesc0 = make_smem_desc(smem_base + A_STAGE_BYTES, p.b_mn ? BLOCK_K * 128 : 16);
+      const uint32_t stage16 = stage_bytes >> 4;
+      const bool wait_full = dbg != 1 && dbg != 2, do_mma = dbg != 3 && dbg != 5;
+      const uint32_t idesc = p.idesc;
       for (int w = group; w < p.num_work; w += ngroups) {
         const Work t = decode_work(p, w, 0, per_unit);
         mbar_wait(tempty_bar(as), aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+        uint32_t accum = 0;
         for (int kit = t.k_begin; kit < t.k_end; kit++) {
-          if (p.dbg != 1 && p.dbg != 2) mbar_wait(full_bar(s), ph);
+          if (wait_full) mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + A_STAGE_BYTES;
+          const uint64_t ad = adesc0 + (uint64_t)(s * stage16), bd = bdesc0 + (uint64_t)(s * stage16);
+          if (do_mma) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-            if (p.dbg == 3) break;  // experiment: operand traffic without MMAs
-            uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo);
-            uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo);
-            if constexpr (CTA2) umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kit > t.k_begin || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kit > t.k_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+              if constexpr (CTA2) umma_bf16_2sm(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, accum);
+              else umma_bf16(tmem_d, ad + k * a_kstep, bd + k * b_kstep, idesc, accum);
+              accum = 1;
+            }
           }
           // frees the smem stage (in both CTAs) once the MMAs above have read it
           if constexpr (CTA2) umma_commit_2sm(empty_bar(s));
@@ -475,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     const Drop dr = make_drop(d.drop_p, p.seed, d.drop_site);
-    const int nchunks = (p.block_n + 31) / 32;
+    const int nchunks = (dbg >= 5) ? 0 : (p.block_n + 31) / 32;  // dbg 5/6: barrier handshake only, nothing read or stored
     const int rsub = lane >> 3, c4 = lane & 7;
     const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
     if constexpr (EPI == EPI_WGRAD) {
@@ -782,6 +821,10 @@ static int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    if (const char* e = getenv("A3T_TC_SMS")) {  // tuning experiments: restrict the persistent grid
+      int v = atoi(e);
+      if (v >= 2 && v < n) n = v;
+    }
   }
   return n;
 }
@@ -975,10 +1018,6 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
   }
   if (const char* e = getenv("A3T_TC_DBGMODE")) p.dbg = atoi(e);
-  if (p.dbg == 4 && !p.b_mn && !cta2 && (b_rows % 32) == 0) {  // re-encode B with quarter-height boxes
-    bbox[1] = b_rows / 4;
-    if (!encode_map(&tmB, B, bdims, bstr, bbox)) return A3T_ERR_UNSUPPORTED;
-  } else if (p.dbg == 4) p.dbg = 0;
   if (getenv("A3T_TC_DEBUG"))
     fprintf(stderr, "gemm_tc: M=%d N=%d K=%d mode=%d cta2=%d bn=%d splits=%d stages=%d work=%d epi=%d\n", d.M, d.N, d.K,
             d.mode, (int)cta2, p.block_n, p.splits, p.stages, p.num_work, epi);
