@@ -188,9 +188,10 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
       store_p4<TP>(P + r * S + j, pv[0], pv[1], pv[2], pv[3]);
       if (dr.on) {
         const unsigned long long idx0 = (unsigned long long)(r * S + j);
-        const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+        bool kp[4];
+        drop_keep4(dr, drop_fold(idx0), kp);
 #pragma unroll
-        for (int e = 0; e < 4; e++) pv[e] = drop_keep32(dr, (lo + e) ^ hif) ? pv[e] * dr.inv_keep : 0.f;
+        for (int e = 0; e < 4; e++) pv[e] = kp[e] ? pv[e] * dr.inv_keep : 0.f;
         store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
       } else if (Pd != P) {
         store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
@@ -221,9 +222,10 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
       load_p4<TP>(P + r * S + j, pv);
       if (dr.on) {
         const unsigned long long idx0 = (unsigned long long)(r * S + j);
-        const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+        bool kp[4];
+        drop_keep4(dr, drop_fold(idx0), kp);
 #pragma unroll
-        for (int e = 0; e < 4; e++) g[e] = drop_keep32(dr, (lo + e) ^ hif) ? g[e] * dr.inv_keep : 0.f;
+        for (int e = 0; e < 4; e++) g[e] = kp[e] ? g[e] * dr.inv_keep : 0.f;
       }
       dot += (g[0] * pv[0] + g[1] * pv[1]) + (g[2] * pv[2] + g[3] * pv[3]);
       *reinterpret_cast<float4*>(row + j) = make_float4(g[0], g[1], g[2], g[3]);

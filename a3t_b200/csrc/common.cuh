@@ -39,10 +39,12 @@ __device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, fl
 }
 
 // ---- stateless dropout mask (bit-identical twin: oracle/a3t_oracle.py::keep_mask) -----------
-// keep(idx) = top 24 bits of a 3-multiply integer hash of (idx, seed, site) >= p * 2^24.  Eight integer
-// instructions per element: the mask is regenerated in every epilogue/backward instead of stored.
+// One 32-bit integer hash of (element-pair index, seed, site) decides TWO consecutive elements: the even
+// element of the pair takes the low 16 bits, the odd one the high 16 bits; keep iff that 16-bit value
+// >= p * 2^16.  About five integer instructions per element: the mask is regenerated in every
+// epilogue/backward instead of stored.
 struct Drop {
-  uint32_t thr;      // keep iff (hash>>8) >= thr ; thr = (uint32)(p * 2^24)
+  uint32_t thr;      // keep iff r16 >= thr ; thr = (uint32)(p * 2^16)
   float inv_keep;    // 1/(1-p)
   uint32_t k0, k1;   // derived from seed and site
   bool on;
@@ -53,7 +55,7 @@ __device__ __forceinline__ Drop make_drop(float p, const unsigned long long* see
   d.thr = 0; d.inv_keep = 1.f; d.k0 = 0; d.k1 = 0;
   if (d.on) {
     unsigned long long seed = *seed_ptr;
-    d.thr = (uint32_t)(p * 16777216.0f);
+    d.thr = (uint32_t)(p * 65536.0f);
     d.inv_keep = 1.0f / (1.0f - p);
     d.k0 = (uint32_t)(seed & 0xFFFFFFFFull) + site * 0x9E3779B9u;
     d.k1 = (uint32_t)(seed >> 32);
@@ -64,11 +66,26 @@ __device__ __forceinline__ Drop make_drop(float p, const unsigned long long* see
 __device__ __host__ __forceinline__ uint32_t drop_fold(unsigned long long idx) {
   return (uint32_t)(idx & 0xFFFFFFFFull) ^ ((uint32_t)(idx >> 32) * 0x85EBCA6Bu);
 }
-__device__ __forceinline__ bool drop_keep32(const Drop& d, uint32_t folded) {
-  uint32_t x = (folded ^ d.k0) * 0x9E3779B1u + d.k1;
+// hash of one element pair (pair = folded index >> 1)
+__device__ __forceinline__ uint32_t drop_hash(const Drop& d, uint32_t pair) {
+  uint32_t x = (pair ^ d.k0) * 0x9E3779B1u + d.k1;
   x ^= x >> 16; x *= 0x7FEB352Du;
   x ^= x >> 15; x *= 0x846CA68Bu;
-  return (x >> 8) >= d.thr;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep32(const Drop& d, uint32_t folded) {
+  const uint32_t h = drop_hash(d, folded >> 1);
+  return ((folded & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= d.thr;
+}
+// keep flags of the 4 consecutive elements whose folded indices are f0 ^ 0..3 (element index % 4 == 0)
+__device__ __forceinline__ void drop_keep4(const Drop& d, uint32_t f0, bool (&k)[4]) {
+  uint32_t ha = drop_hash(d, f0 >> 1), hb = drop_hash(d, (f0 >> 1) ^ 1u);
+  if (f0 & 1u) {  // only for tensors beyond 2^32 elements: the fold may flip the parity bit
+    ha = __funnelshift_l(ha, ha, 16);
+    hb = __funnelshift_l(hb, hb, 16);
+  }
+  k[0] = (ha & 0xFFFFu) >= d.thr; k[1] = (ha >> 16) >= d.thr;
+  k[2] = (hb & 0xFFFFu) >= d.thr; k[3] = (hb >> 16) >= d.thr;
 }
 __device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
   return drop_keep32(d, drop_fold(idx));

@@ -54,6 +54,8 @@ struct Params {
   int m_tiles;          // total M tiles (per batch entry)
   int m_units;          // scheduling units along M: m_tiles (1-CTA) or ceil(m_tiles / 2) (CTA pairs)
   int n_tiles_per_tap;  // WGRAD: N tiles per tap, else all N tiles
+  int n_step;           // column step of consecutive N tiles (block_n; 64 when a WGRAD tile holds all taps of 64 channels)
+  int wg_alltaps;       // WGRAD: the N tile is (tap, 64 channels) for every tap -> interleaved (c, tap) output rows
   int n_tiles;          // total N tiles
   int k_iters;          // total K iterations of one output tile
   int splits;           // split-K factor (atomics when > 1)
@@ -183,6 +185,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// Weight gradient of a 3-tap conv: the accumulator row holds [tap][64 channels]; the output row is
+// [channel][tap].  Chunk K = floats 32K .. 32K+31 of the interleaved 192-float row (compile-time mapping).
+template <int K>
+__device__ __forceinline__ void wgrad3_chunk(uint32_t taddr_row, float alpha, uint32_t (&out)[32]) {
+  constexpr int CS = (32 * K) / 3;  // first channel touched by this chunk
+  uint32_t a0[16], a1[16], a2[16];
+  tmem_ld16(taddr_row + CS, a0);
+  tmem_ld16(taddr_row + 64 + CS, a1);
+  tmem_ld16(taddr_row + 128 + CS, a2);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const int f = 32 * K + i, c = f / 3 - CS, tp = f % 3;
+    const uint32_t v = tp == 0 ? a0[c] : (tp == 1 ? a1[c] : a2[c]);
+    out[i] = __float_as_uint(alpha * __uint_as_float(v));
+  }
+}
+
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
 //   K-major : 8-row groups 1024 B apart (SBO), LBO unused (=1)
 //   MN-major: 64-element MN atoms `lbo_bytes` apart, 8-k groups 1024 B apart (SBO)
@@ -218,7 +247,7 @@ __device__ __forceinline__ Work decode_work(const Params& p, int w, int rank = 0
   t.seq_idx = m_t / p.m_tiles_per_seq;
   t.m0 = (m_t - t.seq_idx * p.m_tiles_per_seq) * BLOCK_M;
   t.tap_n = n_t / p.n_tiles_per_tap;
-  t.n0 = (n_t - t.tap_n * p.n_tiles_per_tap) * p.block_n;
+  t.n0 = (n_t - t.tap_n * p.n_tiles_per_tap) * p.n_step;
   int per = (p.k_iters + p.splits - 1) / p.splits;
   t.k_begin = split * per;
   t.k_end = min(p.k_iters, t.k_begin + per);
@@ -277,10 +306,11 @@ __device__ __forceinline__ void epilogue4(const Params& p, const Drop& dr, float
   }
   if (dr.on) {
     const unsigned long long idx0 = drow + (unsigned long long)ncol;
-    const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
-    if (lo <= 0xFFFFFFF0u) {
+    if ((idx0 & 3ull) == 0) {
+      bool kp[4];
+      drop_keep4(dr, drop_fold(idx0), kp);
 #pragma unroll
-      for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * dr.inv_keep : 0.f;
+      for (int j = 0; j < 4; j++) v[j] = kp[j] ? v[j] * dr.inv_keep : 0.f;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = drop_keep(dr, idx0 + j) ? v[j] * dr.inv_keep : 0.f;
@@ -326,11 +356,12 @@ __device__ __forceinline__ void epilogue4(const Params& p, const Drop& dr, float
 // EPI_MASK | EPI_DROP | EPI_RES | EPI_BF16 selecting the specialised vectorised epilogue.
 constexpr int EPI_MASK = 1, EPI_DROP = 2, EPI_RES = 4, EPI_BF16 = 8;
 constexpr int EPI_WGRAD = 16;  // fp32 weight-gradient scatter (N, C, taps), optional split-K atomics
+constexpr int EPI_WGRAD_TMA = 17;  // fp32 weight gradient through TMA tensor store / reduce-add (taps 1 or 3)
 
 template <int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -354,6 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    if constexpr (EPI >= 0 && EPI != EPI_WGRAD) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
     for (int s = 0; s < p.stages; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -409,8 +441,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         dj[1] = BLOCK_K; dj[5] = BLOCK_K;
         dw[1] = -p.cblocks * BLOCK_K; dw[2] = 1; dw[5] = -p.cblocks * BLOCK_K; dw[6] = 1;
       } else {
-        dj[p.a_mn ? 1 : 0] = BLOCK_K;
-        dj[p.b_mn ? 5 : 4] = BLOCK_K;
+        dj[0] = p.a_mn ? 0 : BLOCK_K; dj[1] = p.a_mn ? BLOCK_K : 0;
+        dj[4] = p.b_mn ? 0 : BLOCK_K; dj[5] = p.b_mn ? BLOCK_K : 0;
       }
       for (int w = group; w < p.num_work; w += ngroups) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
@@ -444,8 +476,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(fb, stage_bytes);
             for (int q = 0; q < a_boxes; q++)
               tma_load_4d(sa + q * (BLOCK_K * 128), &tmA, fb, c[0] + 64 * q, c[1], c[2], c[3]);
-            for (int q = 0; q < b_boxes; q++)
-              tma_load_4d(sb + q * (BLOCK_K * 128), &tmB, fb, c[4] + 64 * q, c[5], c[6], c[7]);
+            if (p.wg_alltaps) {  // box q = tap q of the same 64 channels: rows shifted by q
+              for (int q = 0; q < b_boxes; q++)
+                tma_load_4d(sb + q * (BLOCK_K * 128), &tmB, fb, c[4], c[5] + q, c[6], c[7]);
+            } else {
+              for (int q = 0; q < b_boxes; q++)
+                tma_load_4d(sb + q * (BLOCK_K * 128), &tmB, fb, c[4] + 64 * q, c[5], c[6], c[7]);
+            }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
 #pragma unroll
@@ -517,6 +554,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nchunks = (dbg >= 5) ? 0 : (p.block_n + 31) / 32;  // dbg 5/6: barrier handshake only, nothing read or stored
     const int rsub = lane >> 3, c4 = lane & 7;
     const int nlim = (d.mode == A3T_GEMM_WGRAD) ? d.cin : d.N;
+    if constexpr (EPI == EPI_WGRAD_TMA) {
+      // ---- weight gradient, fp32 (N, C, taps) with taps innermost: thread = row, 32-float chunks of the
+      // output row staged in 128B-swizzled shared memory, then ONE TMA tensor store (or reduce-add when
+      // the K range is split over CTAs) per chunk: no scalar atomics, full-line requests ----
+      const float alpha = d.alpha;
+      const bool reduce = p.splits > 1;
+      const uint32_t stg_row = stg + lane * 128;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      const int nch = (dbg >= 5) ? 0 : (p.wg_alltaps ? 6 : (p.block_n + 31) / 32);
+      for (int w = group; w < p.num_work; w += ngroups) {
+        const Work t = decode_work(p, w, (int)rank, per_unit);
+        const int trow0 = t.m0 + q * 32;
+        const uint32_t taddr_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+        const int fcol0 = p.wg_alltaps ? t.n0 * 3 : t.n0;  // first float of this tile inside the output row
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+        for (int k = half; k < nch; k += NUM_EPI_WARPS / 4) {
+          uint32_t out[32];
+          if (p.wg_alltaps) {
+            switch (k) {
+              case 0: wgrad3_chunk<0>(taddr_row, alpha, out); break;
+              case 1: wgrad3_chunk<1>(taddr_row, alpha, out); break;
+              case 2: wgrad3_chunk<2>(taddr_row, alpha, out); break;
+              case 3: wgrad3_chunk<3>(taddr_row, alpha, out); break;
+              case 4: wgrad3_chunk<4>(taddr_row, alpha, out); break;
+              default: wgrad3_chunk<5>(taddr_row, alpha, out); break;
+            }
+          } else {
+            tmem_ld32(taddr_row + k * 32, out);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) out[i] = __float_as_uint(alpha * __uint_as_float(out[i]));
+          }
+          if (k + NUM_EPI_WARPS / 4 >= nch) {  // all TMEM reads of this warp are done: hand the stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ sw) << 4)), "r"(out[4 * u]),
+                         "r"(out[4 * u + 1]), "r"(out[4 * u + 2]), "r"(out[4 * u + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = fcol0 + 32 * k;
+            if (reduce)
+              asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                               (uint64_t)&tmC),
+                           "r"(stg), "r"(c0), "r"(trow0), "r"(0), "r"(0)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                               (uint64_t)&tmC),
+                           "r"(stg), "r"(c0), "r"(trow0), "r"(0), "r"(0)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (nch <= half) {  // this warp had no chunk: still release the accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else
     if constexpr (EPI == EPI_WGRAD) {
       // ---- weight gradient: C[m, (tap, c)] fp32 at m*sc_m + tap*sc_tap + c*sc_n, alpha only ----
       const float alpha = d.alpha;
@@ -585,39 +693,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else
     if constexpr (EPI >= 0) {
-      // ---- specialised path: PLAIN/CONV, unit column stride, N % 4 == 0, 16-byte aligned rows ----
+      // ---- specialised path (PLAIN/CONV, unit column stride): thread = row.  A "superchunk" is the span
+      // of columns whose output is 128 bytes per row (32 fp32 / 64 bf16): tcgen05.ld -> bias / ReLU /
+      // mask / dropout / residual in registers -> 128B-swizzled staging rows in shared memory -> one TMA
+      // tensor store per superchunk (the tensor map clips rows and columns outside C, which also
+      // implements the sequence boundary of CONV and the phantom tile of a CTA pair).  Mask and residual
+      // are read straight from global memory by the row's own thread (16-byte loads, L1 keeps the lines). ----
       constexpr bool kMask = EPI & EPI_MASK, kDrop = EPI & EPI_DROP, kRes = EPI & EPI_RES, kBf16 = EPI & EPI_BF16;
+      constexpr int SC_COLS = kBf16 ? 64 : 32;
+      static_assert(!(kRes && kBf16), "residual epilogue is fp32-output only");
       const float alpha = d.alpha, out_scale = d.out_scale, mask_scale = d.mask_scale;
       const bool relu = d.relu != 0;
       const float drop_mul = kDrop ? dr.inv_keep * out_scale : out_scale;
       const int row_lim = (d.mode == A3T_GEMM_CONV) ? d.seq : d.M;
+      const int nsc = (dbg >= 5) ? 0 : (p.block_n + SC_COLS - 1) / SC_COLS;
+      const uint32_t stg_row = stg + lane * 128;
+      const uint32_t sw = (uint32_t)(lane & 7);
       for (int w = group; w < p.num_work; w += ngroups) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
-        const int row0 = t.m0 + q * 32 + rsub;                       // row inside the sequence / matrix
-        const int mrow0 = (d.mode == A3T_GEMM_CONV) ? t.seq_idx * d.seq + row0 : row0;  // row inside C
-        const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)mrow0 * d.sc_m;
-        const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)mrow0 * d.sr_m;
-        const unsigned long long dbase = ((unsigned long long)t.z * d.M + mrow0) * (unsigned long long)d.N;
+        const int trow0 = t.m0 + q * 32;                              // first row of this warp (in sequence / matrix)
+        const int row = trow0 + lane;
+        const int mrow = (d.mode == A3T_GEMM_CONV) ? t.seq_idx * d.seq + row : row;  // row inside C
+        const bool row_ok = row < row_lim && (d.mode != A3T_GEMM_CONV || t.seq_idx * d.seq < d.M);
+        const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)mrow * d.sc_m;
+        const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)mrow * d.sr_m;
+        const unsigned long long dbase = ((unsigned long long)t.z * d.M + mrow) * (unsigned long long)d.N;
+        const int cc2 = (d.mode == A3T_GEMM_CONV) ? t.seq_idx : t.b2, cc3 = (d.mode == A3T_GEMM_CONV) ? 0 : t.b1;
         bool waited = false, released = false;
-        for (int c = half; c < nchunks; c += 2) {
-          const int col = c * 32 + c4 * 4;
-          const int n4 = t.n0 + col;
-          const bool col_ok = col < p.block_n && n4 < d.N && (d.mode != A3T_GEMM_CONV || t.seq_idx * d.seq < d.M);
+        for (int sc = half; sc < nsc; sc += NUM_EPI_WARPS / 4) {
+          const int n0c = t.n0 + sc * SC_COLS;
           // operands of the epilogue that live in global memory: issue the loads before waiting on TMEM
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && col_ok) bias4 = __ldg((const float4*)(p.bias + n4));
-          float4 rv[8];
-          uint2 mk[8];
+          float4 rv[kRes ? SC_COLS / 4 : 1];
+          uint4 mk[kMask ? SC_COLS / 8 : 1];
+          if constexpr (kRes) {
 #pragma unroll
-          for (int it = 0; it < 8; it++) {
-            const bool ok = col_ok && (row0 + it * 4) < row_lim;
-            if constexpr (kRes) {
-              rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok) rv[it] = __ldg((const float4*)(p.res + rbase + (int64_t)it * 4 * d.sr_m + n4));
+            for (int g4 = 0; g4 < SC_COLS / 4; g4++) {
+              rv[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_ok && n0c + 4 * g4 < d.N) rv[g4] = __ldg((const float4*)(p.res + rbase + n0c + 4 * g4));
             }
-            if constexpr (kMask) {
-              mk[it] = make_uint2(0u, 0u);
-              if (ok) mk[it] = __ldg((const uint2*)((const __nv_bfloat16*)p.mask + cbase + (int64_t)it * 4 * d.sc_m + n4));
+          }
+          if constexpr (kMask) {
+#pragma unroll
+            for (int g8 = 0; g8 < SC_COLS / 8; g8++) {
+              mk[g8] = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok && n0c + 8 * g8 < d.N) mk[g8] = __ldg((const uint4*)((const __nv_bfloat16*)p.mask + cbase + n0c + 8 * g8));
             }
           }
           if (!waited) {
@@ -625,68 +744,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             waited = true;
           }
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + c * 32, acc);
+          uint32_t acc[SC_COLS];
+          {
+            const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + sc * SC_COLS;
+            tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+            if constexpr (SC_COLS == 64) tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          }
           tmem_ld_wait();
-          if (c + 2 >= nchunks) {
+          if (sc + NUM_EPI_WARPS / 4 >= nsc) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
             released = true;
           }
 #pragma unroll
-          for (int g4 = 0; g4 < 8; g4++)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((g4 ^ (lane & 7)) << 4)),
-                         "r"(acc[4 * g4]), "r"(acc[4 * g4 + 1]), "r"(acc[4 * g4 + 2]), "r"(acc[4 * g4 + 3])
-                         : "memory");
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 8; it++) {
-            const int R = it * 4 + rsub;
-            float4 a;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                         : "r"(stg + R * 128 + ((c4 ^ (R & 7)) << 4))
-                         : "memory");
-            float v[4] = {fmaf(alpha, a.x, bias4.x), fmaf(alpha, a.y, bias4.y), fmaf(alpha, a.z, bias4.z),
-                          fmaf(alpha, a.w, bias4.w)};
+          for (int g4 = 0; g4 < SC_COLS / 4; g4++) {
+            const int n4 = n0c + 4 * g4;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && n4 < d.N) bias4 = __ldg((const float4*)(p.bias + n4));  // same address in every lane
+            float v[4] = {fmaf(alpha, __uint_as_float(acc[4 * g4]), bias4.x), fmaf(alpha, __uint_as_float(acc[4 * g4 + 1]), bias4.y),
+                          fmaf(alpha, __uint_as_float(acc[4 * g4 + 2]), bias4.z), fmaf(alpha, __uint_as_float(acc[4 * g4 + 3]), bias4.w)};
             if (relu) {
 #pragma unroll
               for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
             }
             if constexpr (kMask) {
-              const __nv_bfloat16* mb = (const __nv_bfloat16*)&mk[it];
+              const uint32_t* mw = reinterpret_cast<const uint32_t*>(&mk[g4 >> 1]) + 2 * (g4 & 1);
 #pragma unroll
-              for (int j = 0; j < 4; j++) v[j] = (__bfloat162float(mb[j]) != 0.f) ? v[j] * mask_scale : 0.f;
+              for (int j = 0; j < 4; j++) {
+                const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
+                v[j] = (bits & 0x7FFFu) ? v[j] * mask_scale : 0.f;   // bf16 +-0 -> masked
+              }
             }
             if constexpr (kDrop) {
-              const unsigned long long idx0 = dbase + (unsigned long long)it * 4ull * (unsigned long long)d.N + n4;
-              const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
-              if (lo <= 0xFFFFFFF0u) {
+              bool kp[4];  // N % 4 == 0 and n4 % 4 == 0 on this path: the element index is a multiple of 4
+              drop_keep4(dr, drop_fold(dbase + (unsigned long long)n4), kp);
 #pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * drop_mul : 0.f;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = drop_keep(dr, idx0 + j) ? v[j] * drop_mul : 0.f;
-              }
+              for (int j = 0; j < 4; j++) v[j] = kp[j] ? v[j] * drop_mul : 0.f;
             } else {
 #pragma unroll
               for (int j = 0; j < 4; j++) v[j] *= out_scale;
             }
             if constexpr (kRes) {
-              v[0] += rv[it].x; v[1] += rv[it].y; v[2] += rv[it].z; v[3] += rv[it].w;
+              v[0] += rv[g4].x; v[1] += rv[g4].y; v[2] += rv[g4].z; v[3] += rv[g4].w;
             }
-            if (col_ok && (row0 + it * 4) < row_lim) {
-              const int64_t coff = cbase + (int64_t)it * 4 * d.sc_m + n4;
-              if constexpr (kBf16) {
-                __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v[0], v[1]), __floats2bfloat162_rn(v[2], v[3])};
-                *(uint2*)((__nv_bfloat16*)p.C + coff) = *(const uint2*)h;
-              } else {
-                *(float4*)((float*)p.C + coff) = make_float4(v[0], v[1], v[2], v[3]);
-              }
+            if constexpr (kBf16) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              acc[2 * g4] = *reinterpret_cast<uint32_t*>(&h0);       // packed in place: unit u = acc[4u .. 4u+3]
+              acc[2 * g4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; j++) acc[4 * g4 + j] = __float_as_uint(v[j]);
             }
           }
+          // the previous TMA store of this warp must have finished READING the staging rows
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ sw) << 4)), "r"(acc[4 * u]),
+                         "r"(acc[4 * u + 1]), "r"(acc[4 * u + 2]), "r"(acc[4 * u + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                             (uint64_t)&tmC),
+                         "r"(stg), "r"(n0c), "r"(trow0), "r"(cc2), "r"(cc3)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
         if (!waited) {
           mbar_wait(tfull_bar(as), aph);
@@ -699,6 +826,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (++as == 2) { as = 0; aph ^= 1; }
       }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
     } else
     for (int w = group; w < p.num_work; w += ngroups) {
       const Work t = decode_work(p, w, (int)rank, per_unit);
@@ -793,9 +921,9 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 4-D bf16 tensor map: dims[0] contiguous; strides in elements for dims 1..3
+// 4-D tensor map (bf16, or fp32 when esize == 4): dims[0] contiguous; strides in elements for dims 1..3
 static bool encode_map(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3],
-                       const int box[4]) {
+                       const int box[4], int esize = 2) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gd[4], gs[3];
@@ -804,10 +932,10 @@ static bool encode_map(CUtensorMap* map, const void* base, const int64_t dims[4]
     gd[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
   }
-  for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides[i] * 2;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides[i] * esize;
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -907,21 +1035,28 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   const bool plain_epi = !bias && !res && !mask && d.drop_p == 0.f && !d.relu;
   const bool can_split = d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && d.sc_tap == 1 &&
                          d.sc_n == d.taps && d.sc_m == (int64_t)d.taps * d.cin;
+  // WGRAD through TMA store / reduce-add: output rows are contiguous (c, tap) runs of fp32
+  const char* env_cta = getenv("A3T_TC_CTA");  // "1" / "2": force single-CTA / CTA-pair tiles (experiments)
+  const bool force_pair = env_cta && atoi(env_cta) == 2;
+  const bool wg_tma = can_split && (d.taps == 1 || (d.taps == 3 && !force_pair)) && ((int64_t)d.cin * d.taps) % 4 == 0 &&
+                      al16(C) && !getenv("A3T_TC_GENERIC_EPI") && !getenv("A3T_TC_WGRAD_ATOMIC");
+  const bool wg3 = wg_tma && d.taps == 3;  // N tile = 3 taps x 64 channels (single-CTA tiles only)
   int best_bn = 0, best_split = 1, best_cta2 = 0;
   double best_cost = 1e30;
   const int cands[5] = {256, 192, 128, 64, ((nlim + 15) / 16) * 16};
-  const char* env_cta = getenv("A3T_TC_CTA");  // "1" / "2": force single-CTA / CTA-pair tiles (experiments)
   for (int cta2 = 0; cta2 <= 1; cta2++) {
     // measured on B200 (tools/bench_gemm2.py): CTA pairs are not faster than single CTAs for these shapes
     // (61.9 vs 61.1 us on FFN w_1), so pairs are opt-in until the main loop is no longer delivery-bound
     if (env_cta ? atoi(env_cta) != cta2 + 1 : cta2 != 0) continue;
     if (cta2 && p.m_tiles < 2) continue;
+    if (cta2 && wg3) continue;
     for (int ci = 0; ci < 5; ci++) {
       int bn = cands[ci];
       if (bn > 256 || bn < 16) continue;
+      if (wg3 && bn != 192) continue;
       if (p.b_mn && (bn % (cta2 ? 128 : 64))) continue;
       if (cta2 && (bn % 32)) continue;
-      int nt = ceil_div(nlim, bn) * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
+      int nt = wg3 ? ceil_div(nlim, 64) : ceil_div(nlim, bn) * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
       int64_t units = (int64_t)(cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt * nbatch;
       int groups = cta2 ? sms / 2 : sms;
       int max_split = can_split ? (p.k_iters / 16 < 1 ? 1 : p.k_iters / 16) : 1;
@@ -941,14 +1076,18 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   if (const char* e = getenv("A3T_TC_BN")) {  // tuning experiments only
     int v = atoi(e);
     if (v >= 16 && v <= 256 && v % 16 == 0 && !(p.b_mn && v % (best_cta2 ? 128 : 64)) && !(best_cta2 && v % 32)) {
-      best_bn = v;
-      best_split = 1;
+      if (!wg3) {
+        best_bn = v;
+        best_split = 1;
+      }
     }
   }
   const bool cta2 = best_cta2 != 0;
   p.block_n = best_bn;
-  p.n_tiles_per_tap = ceil_div(nlim, p.block_n);
-  p.n_tiles = p.n_tiles_per_tap * (d.mode == A3T_GEMM_WGRAD ? d.taps : 1);
+  p.wg_alltaps = wg3 ? 1 : 0;
+  p.n_step = wg3 ? 64 : p.block_n;
+  p.n_tiles_per_tap = ceil_div(nlim, p.n_step);
+  p.n_tiles = p.n_tiles_per_tap * ((d.mode == A3T_GEMM_WGRAD && !wg3) ? d.taps : 1);
   p.m_units = cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   int64_t tiles = (int64_t)p.m_units * p.n_tiles * nbatch;
   if (tiles * best_split > (1 << 30)) return A3T_ERR_UNSUPPORTED;
@@ -987,20 +1126,47 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
 
   // ---- epilogue class -------------------------------------------------------------------------
   int epi = -1;
-  if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && !getenv("A3T_TC_GENERIC_EPI")) epi = EPI_WGRAD;
-  else if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || p.vec_r) &&
-      (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !getenv("A3T_TC_GENERIC_EPI"))
-    epi = (mask ? EPI_MASK : 0) | (d.drop_p > 0.f ? EPI_DROP : 0) | (res ? EPI_RES : 0) |
-          (d.dtype_c == A3T_BF16 ? EPI_BF16 : 0);
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+  CUtensorMap tmC = tmA;  // placeholder unless the TMA-store epilogue is selected
+  if (wg_tma) {
+    int64_t cdims[4] = {(int64_t)d.cin * d.taps, d.M, 1, 1}, cstr[3] = {d.sc_m, d.sc_m, d.sc_m};
+    int cbox[4] = {32, 32, 1, 1};
+    if (encode_map(&tmC, C, cdims, cstr, cbox, 4)) epi = EPI_WGRAD_TMA;
+  }
+  if (epi >= 0) {
+  } else if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && !wg3 && !getenv("A3T_TC_GENERIC_EPI")) epi = EPI_WGRAD;
+  else if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || (p.vec_r && d.dtype_c == A3T_F32)) &&
+           (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !getenv("A3T_TC_GENERIC_EPI")) {
+    // TMA tensor store of C: (N, rows, batch2 | sequence, batch1); superchunks must not straddle N tiles
+    const int sc_cols = d.dtype_c == A3T_BF16 ? 64 : 32;
+    const int cs = d.dtype_c == A3T_BF16 ? 2 : 4;
+    if (p.block_n % sc_cols == 0 || p.n_tiles == 1) {
+      int64_t cdims[4], cstr[3];
+      int cbox[4] = {sc_cols, 32, 1, 1};
+      cdims[0] = d.N;
+      cstr[0] = d.sc_m;
+      if (d.mode == A3T_GEMM_CONV) {
+        cdims[1] = d.seq; cdims[2] = d.M / d.seq; cdims[3] = 1;
+        cstr[1] = (int64_t)d.seq * d.sc_m; cstr[2] = cstr[1];
+      } else {
+        cdims[1] = d.M; cdims[2] = d.batch2; cdims[3] = d.batch1;
+        cstr[1] = d.batch2 > 1 ? d.sc_b2 : d.sc_m; cstr[2] = d.batch1 > 1 ? d.sc_b1 : d.sc_m;
+      }
+      bool ok = true;
+      for (int i = 0; i < 3; i++) ok = ok && cstr[i] > 0 && cstr[i] < ((int64_t)1 << 37) && ((cstr[i] * cs) % 16) == 0;
+      if (ok && encode_map(&tmC, C, cdims, cstr, cbox, cs))
+        epi = (mask ? EPI_MASK : 0) | (d.drop_p > 0.f ? EPI_DROP : 0) | (res ? EPI_RES : 0) |
+              (d.dtype_c == A3T_BF16 ? EPI_BF16 : 0);
+    }
+  }
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
 #define A3T_ROW(C2)                                                                                               \
   {gemm_tc_kernel<0, C2>,  gemm_tc_kernel<1, C2>,  gemm_tc_kernel<2, C2>,  gemm_tc_kernel<3, C2>,  gemm_tc_kernel<4, C2>,  \
    gemm_tc_kernel<5, C2>,  gemm_tc_kernel<6, C2>,  gemm_tc_kernel<7, C2>,  gemm_tc_kernel<8, C2>,  gemm_tc_kernel<9, C2>,  \
-   gemm_tc_kernel<10, C2>, gemm_tc_kernel<11, C2>, gemm_tc_kernel<12, C2>, gemm_tc_kernel<13, C2>, gemm_tc_kernel<14, C2>, \
-   gemm_tc_kernel<15, C2>, gemm_tc_kernel<EPI_WGRAD, C2>, gemm_tc_kernel<-1, C2>}
-  static const KernelFn table[2][18] = {A3T_ROW(false), A3T_ROW(true)};
-  static bool attr_set[2][18] = {{false}};
-  const int ki = epi < 0 ? 17 : epi;
+   gemm_tc_kernel<10, C2>, gemm_tc_kernel<11, C2>, gemm_tc_kernel<-1, C2>, gemm_tc_kernel<-1, C2>, gemm_tc_kernel<-1, C2>, \
+   gemm_tc_kernel<-1, C2>, gemm_tc_kernel<EPI_WGRAD, C2>, gemm_tc_kernel<EPI_WGRAD_TMA, C2>, gemm_tc_kernel<-1, C2>}
+  static const KernelFn table[2][19] = {A3T_ROW(false), A3T_ROW(true)};
+  static bool attr_set[2][19] = {{false}};
+  const int ki = epi < 0 ? 18 : epi;
   const KernelFn fn = table[cta2 ? 1 : 0][ki];
   if (!attr_set[cta2 ? 1 : 0][ki]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX);
@@ -1041,7 +1207,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmC, p);
     if (e != cudaSuccess) {
       set_error("gemm_tc: launch: %s", cudaGetErrorString(e));
       return A3T_ERR_CUDA;

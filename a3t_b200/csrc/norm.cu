@@ -116,9 +116,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
           g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
         }
         if (dr.on) {
-          const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)((unsigned long long)idx0 >> 32) * 0x85EBCA6Bu;
+          bool kp[4];
+          drop_keep4(dr, drop_fold((unsigned long long)idx0), kp);
 #pragma unroll
-          for (int e = 0; e < 4; e++) g[e] = drop_keep32(dr, (lo + e) ^ hif) ? g[e] : 0.f;
+          for (int e = 0; e < 4; e++) g[e] = kp[e] ? g[e] : 0.f;
         }
         float be[4] = {0.f, 0.f, 0.f, 0.f};
         if (relu) {
@@ -363,9 +364,10 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const fl
 // keep-mask of 4 consecutive elements starting at idx0 (idx0 % 4 == 0)
 __device__ __forceinline__ void drop_apply4(const Drop& dr, unsigned long long idx0, float (&v)[4]) {
   if (!dr.on) return;
-  const uint32_t lo = (uint32_t)idx0, hif = (uint32_t)(idx0 >> 32) * 0x85EBCA6Bu;
+  bool kp[4];
+  drop_keep4(dr, drop_fold(idx0), kp);
 #pragma unroll
-  for (int j = 0; j < 4; j++) v[j] = drop_keep32(dr, (lo + j) ^ hif) ? v[j] * dr.inv_keep : 0.f;
+  for (int j = 0; j < 4; j++) v[j] = kp[j] ? v[j] * dr.inv_keep : 0.f;
 }
 
 template <typename TY>

@@ -40,16 +40,17 @@ def keep_mask(numel: int, p: float, seed: int, site: int) -> torch.Tensor:
         idx = np.arange(numel, dtype=np.uint64)
         lo = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
         hi = (idx >> np.uint64(32)).astype(np.uint32)
-        x = lo ^ (hi * np.uint32(0x85EBCA6B))
+        f = lo ^ (hi * np.uint32(0x85EBCA6B))
         k0 = np.uint32(seed & 0xFFFFFFFF) + np.uint32(site) * np.uint32(0x9E3779B9)
         k1 = np.uint32((seed >> 32) & 0xFFFFFFFF)
-        x = (x ^ k0) * np.uint32(0x9E3779B1) + k1
+        x = ((f >> np.uint32(1)) ^ k0) * np.uint32(0x9E3779B1) + k1   # one hash per element PAIR
         x ^= x >> np.uint32(16)
         x *= np.uint32(0x7FEB352D)
         x ^= x >> np.uint32(15)
         x *= np.uint32(0x846CA68B)
-    thr = np.uint32(np.float32(p) * np.float32(16777216.0))
-    return torch.from_numpy((x >> np.uint32(8)) >= thr)
+        r16 = np.where((f & np.uint32(1)) != 0, x >> np.uint32(16), x & np.uint32(0xFFFF))
+    thr = np.uint32(np.float32(p) * np.float32(65536.0))
+    return torch.from_numpy(r16 >= thr)
 
 
 def _drop(x: torch.Tensor, drop) -> torch.Tensor:
