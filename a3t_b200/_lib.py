@@ -66,7 +66,7 @@ _SIGS = {
     "a3t_qkv4_bias": [_P, _P, _P, _P, _P, _P, _I, _P],
     "a3t_layernorm_fwd": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _F, _I, _F, _F, _P, _U, _P],
     "a3t_layernorm_bwd_blocks": [_L],
-    "a3t_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _U, _P, _I, _F, _F, _U, _P, _P],
     "a3t_colsum_blocks": [_L],
     "a3t_colsum": [_P, _I, _P, _P, _L, _I, _L, _P],
     "a3t_scale_dropout": [_P, _P, _I, _L, _F, _F, _P, _U, _P],

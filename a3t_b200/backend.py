@@ -66,8 +66,31 @@ class CudaBackend:
         self.act_dtype = act_dtype
         self.impl = impl if act_dtype == torch.bfloat16 else _lib.IMPL_SIMT
         self.seed = torch.tensor([seed], dtype=torch.int64, device=self.device)
+        # zero-initialised fp32 arena for the small outputs kernels ACCUMULATE into with atomics (bias / LayerNorm
+        # parameter gradients): one memset per backward pass instead of a second reduction kernel per output.
+        # Slices are valid until the next `begin_backward()`.
+        self._arena = torch.zeros(1 << 20, dtype=torch.float32, device=self.device)
+        self._arena_off = 0
 
     # ------------------------------------------------------------------ helpers
+    def begin_backward(self):
+        """Zero the accumulation arena (called once at the start of graph.backward)."""
+        self._arena.zero_()
+        self._arena_off = 0
+
+    def _zeros(self, n: int) -> torch.Tensor:
+        n4 = (n + 3) & ~3
+        if self._arena_off + n4 > self._arena.numel():
+            return torch.zeros(n, dtype=torch.float32, device=self.device)
+        t = self._arena[self._arena_off:self._arena_off + n]
+        self._arena_off += n4
+        return t
+
+    def owns(self, t: torch.Tensor) -> bool:
+        """True when `t` aliases the accumulation arena (callers that keep it past the step must clone)."""
+        a = self._arena
+        return a.data_ptr() <= t.data_ptr() < a.data_ptr() + a.numel() * 4
+
     def set_seed(self, seed: int):
         self.seed.fill_(seed)
 
@@ -198,6 +221,11 @@ class CudaBackend:
     def colsum(self, x):
         C_ = x.shape[-1]
         rows = x.numel() // C_
+        vn = 8 if x.dtype == torch.bfloat16 else 4
+        if C_ % vn == 0 and x.data_ptr() % 16 == 0:
+            out = self._zeros(C_)  # single kernel, atomics into the zeroed arena
+            call("a3t_colsum", _p(x), _dt(x), _p(out), None, rows, C_, C_, _stream(x))
+            return out
         out = torch.empty(C_, dtype=torch.float32, device=x.device)
         nblk = call("a3t_colsum_blocks", rows)
         partial = torch.empty(nblk * C_, dtype=torch.float32, device=x.device)
@@ -217,18 +245,31 @@ class CudaBackend:
              int(relu), out_scale, p, seed, site, _stream(x))
         return y, mean, rstd
 
-    def ln_bwd(self, dy, x, mean, rstd, gamma, beta, *, relu=False, out_scale=1.0, drop=None, dres=None, eps=None):
+    def ln_bwd(self, dy, x, mean, rstd, gamma, beta, *, relu=False, out_scale=1.0, drop=None, dres=None, eps=None,
+               nxt=None):
+        """Returns (dx, dgamma, dbeta).  With nxt = (scale, drop) also the next backward section's grad prep,
+        fused into the same pass: (dx, dgamma, dbeta, g, gsum) with g = dropout'(dx * scale) in the GEMM dtype
+        and gsum = column sums of g."""
         C_ = x.shape[-1]
         rows = x.numel() // C_
         assert dy.is_contiguous() and x.is_contiguous()
         dx = torch.empty_like(x)
-        dgamma = torch.empty(C_, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(C_, dtype=torch.float32, device=x.device)
-        nblk = call("a3t_layernorm_bwd_blocks", rows)
-        partial = torch.empty(nblk * 2 * C_, dtype=torch.float32, device=x.device)
+        acc = self._zeros((3 if nxt is not None else 2) * C_)
+        dgamma, dbeta = acc[:C_], acc[C_:2 * C_]
         p, seed, site = self._drop(drop)
+        g = gsum = None
+        gscale, gp, gsite = 1.0, 0.0, 0
+        if nxt is not None:
+            gscale = float(nxt[0])
+            gp, gseed, gsite = self._drop(nxt[1])
+            seed = seed or gseed
+            g = torch.empty(x.shape, dtype=self.act_dtype, device=x.device)
+            gsum = acc[2 * C_:]
         call("a3t_layernorm_bwd", _p(dy), _dt(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dres), _p(dx),
-             _p(dgamma), _p(dbeta), _p(partial), rows, C_, int(relu), out_scale, p, seed, site, _stream(x))
+             _p(dgamma), _p(dbeta), None, rows, C_, int(relu), out_scale, p, seed, site, _p(g),
+             _dt(g) if g is not None else A3T_F32, gscale, gp, gsite, _p(gsum), _stream(x))
+        if nxt is not None:
+            return dx, dgamma, dbeta, g, gsum
         return dx, dgamma, dbeta
 
     def scale_dropout(self, x, scale, drop=None, out_dtype=None):

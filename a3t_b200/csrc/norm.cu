@@ -74,22 +74,26 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(
 // LayerNorm backward: warp per row; per-lane dgamma/dbeta register accumulators, block-reduced
 // into partial[blk][2][C]; a second kernel finishes the column sums.
 // ---------------------------------------------------------------------------------------------
-template <typename TDY, int MAXV>
+template <typename TDY, int MAXV, typename TG>
 __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
     const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ dres, float* __restrict__ dx, float* __restrict__ partial, int64_t rows,
     int C, int relu, float out_scale, float drop_p, const unsigned long long* __restrict__ seed,
-    uint32_t site) {
-  extern __shared__ float sm[];  // [LN_WARPS][2][C]
+    uint32_t site, TG* __restrict__ gnext, float gn_scale, float gn_p, uint32_t gn_site,
+    float* __restrict__ acc_dgamma, float* __restrict__ acc_dbeta, float* __restrict__ acc_gsum) {
+  extern __shared__ float sm[];  // [LN_WARPS][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = C >> 2;
   Drop dr = make_drop(drop_p, seed, site);
-  float4 ag[MAXV], ab[MAXV];
+  Drop dn = make_drop(gnext ? gn_p : 0.f, seed, gn_site);
+  const float gn_mul = gn_scale * dn.inv_keep;
+  float4 ag[MAXV], ab[MAXV], an[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; i++) {
     ag[i] = make_float4(0, 0, 0, 0);
     ab[i] = make_float4(0, 0, 0, 0);
+    an[i] = make_float4(0, 0, 0, 0);
   }
   const float scale_keep = out_scale * dr.inv_keep;
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LN_WARPS) {
@@ -160,25 +164,56 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + row * C)[c4] = o;
+        if (gnext) {
+          // the next section's "grad prep" g = dropout'(dx * scale) in its GEMM dtype, and the column sums
+          // of g (that section's bias gradient), produced while dx is still in registers
+          const int64_t idx0 = row * C + c4 * 4;
+          float v[4] = {o.x, o.y, o.z, o.w};
+          if (dn.on) {
+            bool kp[4];
+            drop_keep4(dn, drop_fold((unsigned long long)idx0), kp);
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = kp[e] ? v[e] * gn_mul : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] *= gn_mul;
+          }
+          if constexpr (sizeof(TG) == 2) {
+            __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v[0], v[1]), __floats2bfloat162_rn(v[2], v[3])};
+            *reinterpret_cast<uint2*>(gnext + idx0) = *reinterpret_cast<const uint2*>(h);
+            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+            an[i].x += f0.x; an[i].y += f0.y; an[i].z += f1.x; an[i].w += f1.y;
+          } else {
+            *reinterpret_cast<float4*>(gnext + idx0) = make_float4(v[0], v[1], v[2], v[3]);
+            an[i].x += v[0]; an[i].y += v[1]; an[i].z += v[2]; an[i].w += v[3];
+          }
+        }
       }
     }
   }
-  // block reduce the parameter gradients
-  float* sg = sm + (size_t)warp * 2 * C;
+  // block reduce the parameter gradients (and the column sums of gnext)
+  const int nacc = gnext ? 3 : 2;
+  float* sg = sm + (size_t)warp * 3 * C;
 #pragma unroll
   for (int i = 0; i < MAXV; i++) {
     int c4 = lane + i * 32;
     if (c4 < nv) {
       reinterpret_cast<float4*>(sg)[c4] = ag[i];
       reinterpret_cast<float4*>(sg + C)[c4] = ab[i];
+      reinterpret_cast<float4*>(sg + 2 * C)[c4] = an[i];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < nacc * C; c += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < LN_WARPS; w++) t += sm[(size_t)w * 2 * C + c];
-    partial[(size_t)blockIdx.x * 2 * C + c] = t;
+    for (int w = 0; w < LN_WARPS; w++) t += sm[(size_t)w * 3 * C + c];
+    if (partial) {  // two-stage: a second kernel sums the per-block rows (dgamma, dbeta only)
+      if (c < 2 * C) partial[(size_t)blockIdx.x * 2 * C + c] = t;
+    } else {        // accumulate into zero-initialised outputs
+      float* dst = c < C ? acc_dgamma : (c < 2 * C ? acc_dbeta : acc_gsum);
+      if (dst) atomicAdd(dst + (c % C), t);
+    }
   }
 }
 
@@ -286,7 +321,8 @@ template <> struct Vec16<__nv_bfloat16> {
 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ partial,
-                                                         int64_t rows, int C, int64_t ldx) {
+                                                         int64_t rows, int C, int64_t ldx,
+                                                         float* __restrict__ atomic_out = nullptr) {
   constexpr int N = Vec16<T>::N;
   __shared__ float red[8][32 * N + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -326,7 +362,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
       float t = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; y++) t += red[y][idx];
-      partial[(size_t)blockIdx.y * C + cc] = t;
+      if (atomic_out) atomicAdd(atomic_out + cc, t);
+      else partial[(size_t)blockIdx.y * C + cc] = t;
     }
   }
 }
@@ -668,16 +705,27 @@ extern "C" int a3t_layernorm_bwd_blocks(int64_t rows) {
 extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, const float* beta, const float* dres, float* dx, float* dgamma,
                                  float* dbeta, float* partial, int64_t rows, int C, int relu, float out_scale,
-                                 float drop_p, const unsigned long long* seed, uint32_t site, void* stream) {
-  A3T_REQUIRE(dy && x && mean && rstd && gamma && beta && dx && partial, "layernorm_bwd: null pointer");
+                                 float drop_p, const unsigned long long* seed, uint32_t site, void* gnext,
+                                 int dtype_gnext, float gnext_scale, float gnext_drop_p, uint32_t gnext_site,
+                                 float* gsum, void* stream) {
+  A3T_REQUIRE(dy && x && mean && rstd && gamma && beta && dx, "layernorm_bwd: null pointer");
   A3T_REQUIRE(C % 4 == 0 && C <= 128 * LN_MAXV, "layernorm_bwd: C=%d must be a multiple of 4 and <= %d", C, 128 * LN_MAXV);
   A3T_REQUIRE(drop_p == 0.f || seed, "layernorm_bwd: dropout needs a seed");
+  A3T_REQUIRE(!gnext || gnext_drop_p == 0.f || seed, "layernorm_bwd: dropout needs a seed");
+  A3T_REQUIRE(!(gsum && partial), "layernorm_bwd: gsum needs the accumulate mode (partial == NULL, zero-initialised outputs)");
+  A3T_REQUIRE(!gsum || gnext, "layernorm_bwd: gsum without gnext");
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = a3t_layernorm_bwd_blocks(rows);
-  size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
-#define A3T_LN_BWD(T, MV)                                                                                          \
-  ln_bwd_kernel<T, MV><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx, partial, \
-                                                          rows, C, relu, out_scale, drop_p, seed, site)
+  size_t smem = (size_t)LN_WARPS * 3 * C * sizeof(float);
+#define A3T_LN_BWD2(T, MV, TG)                                                                                       \
+  ln_bwd_kernel<T, MV, TG><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx, partial, \
+                                                              rows, C, relu, out_scale, drop_p, seed, site, (TG*)gnext,  \
+                                                              gnext_scale, gnext_drop_p, gnext_site, dgamma, dbeta, gsum)
+#define A3T_LN_BWD(T, MV)                                        \
+  do {                                                           \
+    if (gnext && dtype_gnext == A3T_BF16) A3T_LN_BWD2(T, MV, __nv_bfloat16); \
+    else A3T_LN_BWD2(T, MV, float);                              \
+  } while (0)
   if (dtype_dy == A3T_BF16) {
     if (C <= 384) A3T_LN_BWD(__nv_bfloat16, 3);
     else A3T_LN_BWD(__nv_bfloat16, 4);
@@ -687,7 +735,7 @@ extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, c
   }
   int rc = check_launch("layernorm_bwd");
   if (rc) return rc;
-  if (dgamma || dbeta) {
+  if (partial && (dgamma || dbeta)) {
     reduce_partial_kernel<<<(2 * C + 127) / 128, 1024, 0, st>>>(partial, dgamma, dbeta, nblk, C);
     rc = check_launch("layernorm_bwd_reduce");
   }
@@ -698,17 +746,23 @@ extern "C" int a3t_colsum_blocks(int64_t rows) { return colsum_blocks_host(rows)
 
 extern "C" int a3t_colsum(const void* x, int dtype_x, float* out, float* partial, int64_t rows, int C, int64_t ldx,
                           void* stream) {
-  A3T_REQUIRE(x && out && partial && C > 0, "colsum: bad args");
+  A3T_REQUIRE(x && out && C > 0, "colsum: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = colsum_blocks_host(rows);
   dim3 grid((C + 255) / 256, nblk);
   const int vn = dtype_x == A3T_BF16 ? 8 : 4;
-  if (C % vn == 0 && ldx % vn == 0 && ((uintptr_t)x & 15) == 0) {
+  const bool vec = C % vn == 0 && ldx % vn == 0 && ((uintptr_t)x & 15) == 0;
+  A3T_REQUIRE(partial || vec, "colsum: the accumulate mode (partial == NULL) needs 16-byte aligned rows");
+  if (vec) {
+    // partial == NULL: one kernel, block sums accumulated into the zero-initialised `out` with atomics
+    if (!partial && nblk > 296) nblk = 296;
     dim3 gv((C / vn + 31) / 32, nblk);
+    float* acc = partial ? nullptr : out;
     if (dtype_x == A3T_BF16)
-      colsum_vec_kernel<__nv_bfloat16><<<gv, 256, 0, st>>>((const __nv_bfloat16*)x, partial, rows, C, ldx);
+      colsum_vec_kernel<__nv_bfloat16><<<gv, 256, 0, st>>>((const __nv_bfloat16*)x, partial, rows, C, ldx, acc);
     else
-      colsum_vec_kernel<float><<<gv, 256, 0, st>>>((const float*)x, partial, rows, C, ldx);
+      colsum_vec_kernel<float><<<gv, 256, 0, st>>>((const float*)x, partial, rows, C, ldx, acc);
+    if (!partial) return check_launch("colsum");
   } else if (dtype_x == A3T_BF16)
     colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, partial, rows, C, ldx);
   else

@@ -122,24 +122,41 @@ def _ffn_fwd(ops, P, wc, pre, norm, x, p_drop, sites, training, ctx):
     return y
 
 
-def _ffn_bwd(ops, P, wc, pre, norm, dy, p_drop, training, ctx, G):
+def _grad_prep(ops, dy, scale, drop, gpre):
+    """g = dropout'(dy * scale) in the GEMM dtype and its column sums: taken from the LayerNorm backward that
+    produced dy when it fused them (`gpre`), else computed here."""
+    if gpre is not None:
+        return gpre
+    g = ops.scale_dropout(dy, scale, drop)
+    return g, ops.colsum(g)
+
+
+def _ln_bwd_next(ops, nxt, *args, **kw):
+    """LayerNorm backward that also emits the NEXT backward section's grad prep when `nxt` = (scale, drop)."""
+    out = ops.ln_bwd(*args, nxt=nxt, **kw)
+    if nxt is None:
+        return out[0], out[1], out[2], None
+    return out[0], out[1], out[2], (out[3], out[4])
+
+
+def _ffn_bwd(ops, P, wc, pre, norm, dy, p_drop, training, ctx, G, gpre=None, nxt=None):
     ff = "feed_forward_macaron" if norm == "norm_ff_macaron" else "feed_forward"
     w1 = wc.packed(ops, f"{pre}.{ff}.w_1", [P[f"{pre}.{ff}.w_1.weight"]], None)
     w2 = wc.packed(ops, f"{pre}.{ff}.w_2", [P[f"{pre}.{ff}.w_2.weight"]], None)
     x, h, u = ctx[f"{ff}.x"], ctx[f"{ff}.h"], ctx[f"{ff}.u"]
     d1, d2 = _drop(p_drop, ctx[f"{ff}.s1"], training), _drop(p_drop, ctx[f"{ff}.s2"], training)
-    g = ops.scale_dropout(dy, 0.5, d2)
-    G[f"{pre}.{ff}.w_2.bias"] = ops.colsum(g)
+    g, gsum = _grad_prep(ops, dy, 0.5, d2, gpre)
+    G[f"{pre}.{ff}.w_2.bias"] = gsum
     G[f"{pre}.{ff}.w_2.weight"] = ops.conv_wgrad(g, u, w2.taps)
     inv_keep = 1.0 / (1.0 - p_drop) if d1 is not None else 1.0
     du = ops.conv_dgrad(g, w2, mask=u, mask_scale=inv_keep)
     G[f"{pre}.{ff}.w_1.bias"] = ops.colsum(du)
     G[f"{pre}.{ff}.w_1.weight"] = ops.conv_wgrad(du, h, w1.taps)
     dh = ops.conv_dgrad(du, w1)
-    dx, dg, db = ops.ln_bwd(dh, x, ctx[f"{ff}.mean"], ctx[f"{ff}.rstd"], P[f"{pre}.{norm}.weight"],
-                            P[f"{pre}.{norm}.bias"], dres=dy, eps=1e-12)
+    dx, dg, db, gn = _ln_bwd_next(ops, nxt, dh, x, ctx[f"{ff}.mean"], ctx[f"{ff}.rstd"], P[f"{pre}.{norm}.weight"],
+                                  P[f"{pre}.{norm}.bias"], dres=dy, eps=1e-12)
     G[f"{pre}.{norm}.weight"], G[f"{pre}.{norm}.bias"] = dg, db
-    return dx
+    return dx, gn
 
 
 def _qkv4_weight(P, pre):
@@ -179,7 +196,7 @@ def _mha_fwd(ops, P, wc, pre, x, pos_d, keymask, cfg_H, p_drop, p_att, sites, tr
     return y
 
 
-def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G):
+def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G, gpre=None, nxt=None):
     a = f"{pre}.self_attn"
     x, h, qkv4, pp = ctx["mha.x"], ctx["mha.h"], ctx["mha.qkv4"], ctx["mha.pp"]
     Pm, Pd, cx = ctx["mha.P"], ctx["mha.Pd"], ctx["mha.cx"]
@@ -191,8 +208,8 @@ def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G)
                                                         f"{a}.pos_bias_u", f"{a}.pos_bias_v"]], None)
     wpos = wc.packed(ops, f"{a}.linear_pos", [P[f"{a}.linear_pos.weight"]], None)
     wo = wc.packed(ops, f"{a}.linear_out", [P[f"{a}.linear_out.weight"]], None)
-    g = ops.scale_dropout(dy, 1.0, _drop(p_drop, ctx["mha.s_out"], training))
-    G[f"{a}.linear_out.bias"] = ops.colsum(g)
+    g, gsum = _grad_prep(ops, dy, 1.0, _drop(p_drop, ctx["mha.s_out"], training), gpre)
+    G[f"{a}.linear_out.bias"] = gsum
     G[f"{a}.linear_out.weight"] = ops.conv_wgrad(g, cx, 1).squeeze(-1)
     dcx = ops.conv_dgrad(g, wo)
     dqkv4 = torch.empty_like(qkv4)
@@ -213,10 +230,10 @@ def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G)
     G[f"{a}.pos_bias_u"] = db4[0:D].reshape(H, D // H)
     G[f"{a}.pos_bias_v"] = db4[D:2 * D].reshape(H, D // H)
     dh = ops.conv_dgrad(dqkv4, w4)
-    dx, dg, db = ops.ln_bwd(dh, x, ctx["mha.mean"], ctx["mha.rstd"], P[f"{pre}.norm_mha.weight"],
-                            P[f"{pre}.norm_mha.bias"], dres=dy, eps=1e-12)
+    dx, dg, db, gn = _ln_bwd_next(ops, nxt, dh, x, ctx["mha.mean"], ctx["mha.rstd"], P[f"{pre}.norm_mha.weight"],
+                                  P[f"{pre}.norm_mha.bias"], dres=dy, eps=1e-12)
     G[f"{pre}.norm_mha.weight"], G[f"{pre}.norm_mha.bias"] = dg, db
-    return dx
+    return dx, gn
 
 
 def _convmod_fwd(ops, P, wc, pre, x, p_drop, sites, training, ctx):
@@ -237,13 +254,13 @@ def _convmod_fwd(ops, P, wc, pre, x, p_drop, sites, training, ctx):
     return y
 
 
-def _convmod_bwd(ops, P, wc, pre, dy, p_drop, training, ctx, G):
+def _convmod_bwd(ops, P, wc, pre, dy, p_drop, training, ctx, G, gpre=None, nxt=None):
     c = f"{pre}.conv_module"
     w1 = wc.packed(ops, f"{c}.pw1", [P[f"{c}.pointwise_conv1.weight"]], None)
     w2 = wc.packed(ops, f"{c}.pw2", [P[f"{c}.pointwise_conv2.weight"]], None)
     x, h, u, z, act = ctx["cm.x"], ctx["cm.h"], ctx["cm.u"], ctx["cm.z"], ctx["cm.act"]
-    g = ops.scale_dropout(dy, 1.0, _drop(p_drop, ctx["cm.s"], training))
-    G[f"{c}.pointwise_conv2.bias"] = ops.colsum(g)
+    g, gsum = _grad_prep(ops, dy, 1.0, _drop(p_drop, ctx["cm.s"], training), gpre)
+    G[f"{c}.pointwise_conv2.bias"] = gsum
     G[f"{c}.pointwise_conv2.weight"] = ops.conv_wgrad(g, act, 1)
     dact = ops.conv_dgrad(g, w2, out_dtype=torch.float32)
     dz, dgam, dbet = ops.bn_act_bwd(dact, z, ctx["cm.bm"], ctx["cm.br"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"],
@@ -255,10 +272,10 @@ def _convmod_bwd(ops, P, wc, pre, dy, p_drop, training, ctx, G):
     G[f"{c}.pointwise_conv1.bias"] = ops.colsum(du)
     G[f"{c}.pointwise_conv1.weight"] = ops.conv_wgrad(du, h, 1)
     dh = ops.conv_dgrad(du, w1)
-    dx, dg, dbb = ops.ln_bwd(dh, x, ctx["cm.mean"], ctx["cm.rstd"], P[f"{pre}.norm_conv.weight"],
-                             P[f"{pre}.norm_conv.bias"], dres=dy, eps=1e-12)
+    dx, dg, dbb, gn = _ln_bwd_next(ops, nxt, dh, x, ctx["cm.mean"], ctx["cm.rstd"], P[f"{pre}.norm_conv.weight"],
+                                   P[f"{pre}.norm_conv.bias"], dres=dy, eps=1e-12)
     G[f"{pre}.norm_conv.weight"], G[f"{pre}.norm_conv.bias"] = dg, dbb
-    return dx
+    return dx, gn
 
 
 def _layer_fwd(ops, P, wc, pre, x, pos_d, keymask, H, p_drop, p_att, sites, training, ctx):
@@ -273,13 +290,17 @@ def _layer_fwd(ops, P, wc, pre, x, pos_d, keymask, H, p_drop, p_att, sites, trai
 
 
 def _layer_bwd(ops, P, wc, pre, dy, pos_d, H, p_drop, p_att, training, ctx, G):
-    dx, dg, db = ops.ln_bwd(dy, ctx["fin.x"], ctx["fin.mean"], ctx["fin.rstd"], P[f"{pre}.norm_final.weight"],
-                            P[f"{pre}.norm_final.bias"], eps=1e-12)
+    # every LayerNorm backward also produces the grad prep (scaled / dropped bf16 copy + bias-gradient column
+    # sums) of the section that consumes its dx next, so that section starts directly with its GEMMs
+    nxt = lambda scale, site: (scale, _drop(p_drop, site, training))
+    dx, dg, db, g = _ln_bwd_next(ops, nxt(0.5, ctx["feed_forward.s2"]), dy, ctx["fin.x"], ctx["fin.mean"],
+                                 ctx["fin.rstd"], P[f"{pre}.norm_final.weight"], P[f"{pre}.norm_final.bias"], eps=1e-12)
     G[f"{pre}.norm_final.weight"], G[f"{pre}.norm_final.bias"] = dg, db
-    dx = _ffn_bwd(ops, P, wc, pre, "norm_ff", dx, p_drop, training, ctx, G)
-    dx = _convmod_bwd(ops, P, wc, pre, dx, p_drop, training, ctx, G)
-    dx = _mha_bwd(ops, P, wc, pre, dx, pos_d, H, p_drop, p_att, training, ctx, G)
-    dx = _ffn_bwd(ops, P, wc, pre, "norm_ff_macaron", dx, p_drop, training, ctx, G)
+    dx, g = _ffn_bwd(ops, P, wc, pre, "norm_ff", dx, p_drop, training, ctx, G, gpre=g, nxt=nxt(1.0, ctx["cm.s"]))
+    dx, g = _convmod_bwd(ops, P, wc, pre, dx, p_drop, training, ctx, G, gpre=g, nxt=nxt(1.0, ctx["mha.s_out"]))
+    dx, g = _mha_bwd(ops, P, wc, pre, dx, pos_d, H, p_drop, p_att, training, ctx, G, gpre=g,
+                     nxt=nxt(0.5, ctx["feed_forward_macaron.s2"]))
+    dx, _ = _ffn_bwd(ops, P, wc, pre, "norm_ff_macaron", dx, p_drop, training, ctx, G, gpre=g)
     return dx
 
 
@@ -395,6 +416,8 @@ def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: t
     sv = ctx.saved
     training = ctx.training
     G: Dict[str, torch.Tensor] = {}
+    if hasattr(ops, "begin_backward"):
+        ops.begin_backward()  # zeroes the arena the small gradient outputs are accumulated into
     speech, masked = sv["speech"], sv["masked"]
     before, after = sv["before"], sv["after"]
     Ts, Tt = sv["Ts"], sv["Tt"]

@@ -200,7 +200,9 @@ class _A3TFunction(torch.autograd.Function):
         G = graph.backward(ctx.ops, ctx.P, model._wcache, model.cfg, ctx.sctx, gl.float().contiguous(),
                            dbefore_ext=gbefore, dafter_ext=gafter if ctx.sctx.saved["after"] is not None else None)
         ctx.sctx = None
-        grads = tuple(G.get(n) for n in ctx.names)
+        # small gradients live in the backend's per-step accumulation arena: autograd keeps what we return
+        owns = getattr(ctx.ops, "owns", None)
+        grads = tuple((G[n].clone() if owns is not None and owns(G[n]) else G[n]) if n in G else None for n in ctx.names)
         return (None, None, None, None) + grads
 
 

@@ -155,7 +155,7 @@ class ClockSampler:
 
 
 # kernels launched by one C-ABI call (for gpu_launches)
-KERNELS_PER_CALL = {"a3t_layernorm_bwd": 2, "a3t_colsum": 2, "a3t_mask_input_bwd": 2, "a3t_bn_stats": 2,
+KERNELS_PER_CALL = {"a3t_layernorm_bwd": 1, "a3t_colsum": 1, "a3t_mask_input_bwd": 2, "a3t_bn_stats": 2,
                     "a3t_bn_act_bwd": 3, "a3t_glu_dwconv_bwd": 2, "a3t_masked_l1_fwd": 2, "a3t_grad_sqnorm": 2,
                     "a3t_adam_step": 2, "a3t_relpos_softmax_bwd": 2, "a3t_stft_logmel": 2}
 

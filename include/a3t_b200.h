@@ -125,17 +125,25 @@ int a3t_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
                       float* mean, float* rstd, int64_t rows, int C, float eps, int relu,
                       float out_scale, float drop_p, const unsigned long long* seed, uint32_t site,
                       void* stream);
-/* dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are written (not accumulated) from `partial`
- * (fp32 workspace of 2*nblk*C floats; nblk = a3t_layernorm_bwd_blocks(rows)). dy has dtype_dy. */
+/* dx = (dres ? dres : 0) + LN'(dy).  dy has dtype_dy.
+ * dgamma / dbeta: with `partial` (fp32 workspace of 2*nblk*C floats; nblk = a3t_layernorm_bwd_blocks(rows))
+ * they are WRITTEN by a second reduction kernel; with partial == NULL they are ACCUMULATED with atomics
+ * into caller-zeroed buffers (single kernel).
+ * Optional fused "grad prep" of the next backward section (the residual branch that consumes dx,
+ * conformer/encoder_layer.py:120-165): gnext (dtype_gnext) = dropout'(dx * gnext_scale) with the keep
+ * mask of (gnext_drop_p, gnext_site), and gsum[c] += sum_rows gnext[r,c] (accumulate mode only) --
+ * the bias gradient of the layer whose output that branch scaled. */
 int a3t_layernorm_bwd_blocks(int64_t rows);
 int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, const float* dres,
                       float* dx, float* dgamma, float* dbeta, float* partial, int64_t rows, int C,
                       int relu, float out_scale, float drop_p, const unsigned long long* seed,
-                      uint32_t site, void* stream);
+                      uint32_t site, void* gnext, int dtype_gnext, float gnext_scale,
+                      float gnext_drop_p, uint32_t gnext_site, float* gsum, void* stream);
 
 /* Column sums out[c] = sum_r x[r,c] (bias gradients); `partial` = nblk*C floats workspace with
- * nblk = a3t_colsum_blocks(rows). */
+ * nblk = a3t_colsum_blocks(rows).  partial == NULL: single kernel, block sums are ACCUMULATED into
+ * the caller-zeroed `out` with atomics (needs 16-byte aligned rows: C, ldx multiples of 16 bytes). */
 int a3t_colsum_blocks(int64_t rows);
 int a3t_colsum(const void* x, int dtype_x, float* out, float* partial, int64_t rows, int C,
                int64_t ldx, void* stream);

@@ -76,11 +76,15 @@ class OracleBackend:
         rstd = torch.rsqrt(x.var(-1, unbiased=False) + eps).reshape(-1)
         return y, mean, rstd
 
-    def ln_bwd(self, dy, x, mean, rstd, gamma, beta, *, relu=False, out_scale=1.0, drop=None, dres=None, eps=None):
+    def ln_bwd(self, dy, x, mean, rstd, gamma, beta, *, relu=False, out_scale=1.0, drop=None, dres=None, eps=None,
+               nxt=None):
         dx, dg, db = _vjp(lambda a, g, b: O.ln_fwd(a, g, b, eps, relu=relu, out_scale=out_scale, drop=self._d(drop)),
                           [x, gamma, beta], dy)
         if dres is not None:
             dx = dx + dres
+        if nxt is not None:  # the next backward section's grad prep (fused into the CUDA kernel)
+            g = O.scale_dropout(dx, nxt[0], self._d(nxt[1]))
+            return dx, dg, db, g, g.reshape(-1, g.shape[-1]).sum(0)
         return dx, dg, db
 
     def scale_dropout(self, x, scale, drop=None, out_dtype=None):

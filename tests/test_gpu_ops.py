@@ -77,6 +77,38 @@ def test_layernorm(be, ob, C, rows):
             close(dbc, dbo, atol=2e-3, rtol=1e-3)
 
 
+def test_layernorm_bwd_fused_grad_prep(be, ob):
+    """ln_bwd(nxt=(scale, drop)) also emits the next backward section's g = dropout'(dx*scale) and its column
+    sums; the keep pattern must be bit-identical to the oracle's and the two-stage (`partial`) C-ABI mode must
+    agree with the accumulate mode."""
+    from a3t_b200 import _lib
+
+    C, rows = 384, 211
+    x, gam, bet, dy, dres = g(rows, C, seed=1, scale=2.0), 1 + 0.2 * g(C, seed=2), 0.1 * g(C, seed=3), g(rows, C, seed=4), g(rows, C, seed=5)
+    yo, mo, ro = ob.ln_fwd(x, gam, bet, 1e-12)
+    dxo, dgo, dbo, go, gso = ob.ln_bwd(dy, x, mo, ro, gam, bet, dres=dres, eps=1e-12, nxt=(0.5, (0.2, 11)))
+    be.begin_backward()
+    xc, mc, rc = x.cuda(), mo.cuda(), ro.cuda()
+    dxc, dgc, dbc, gc, gsc = be.ln_bwd(dy.cuda(), xc, mc, rc, gam.cuda(), bet.cuda(), dres=dres.cuda(), eps=1e-12,
+                                       nxt=(0.5, (0.2, 11)))
+    close(dxc, dxo, atol=5e-4, rtol=1e-3)
+    close(dgc, dgo, atol=2e-3, rtol=1e-3)
+    close(dbc, dbo, atol=2e-3, rtol=1e-3)
+    assert torch.equal(gc.cpu() == 0, go == 0)
+    close(gc, go, atol=5e-4, rtol=1e-3)
+    close(gsc, gso, atol=2e-3, rtol=1e-3)
+    # two-stage mode of the C-ABI (workspace given): dgamma / dbeta written, not accumulated
+    nblk = _lib.call("a3t_layernorm_bwd_blocks", rows)
+    partial = torch.empty(nblk * 2 * C, device="cuda")
+    dg2, db2, dx2 = torch.full((C,), 7.0, device="cuda"), torch.full((C,), 7.0, device="cuda"), torch.empty_like(xc)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("a3t_layernorm_bwd", dy.cuda().data_ptr(), _lib.A3T_F32, xc.data_ptr(), mc.data_ptr(), rc.data_ptr(),
+              gam.cuda().data_ptr(), bet.cuda().data_ptr(), None, dx2.data_ptr(), dg2.data_ptr(), db2.data_ptr(),
+              partial.data_ptr(), rows, C, 0, 1.0, 0.0, None, 0, None, _lib.A3T_F32, 1.0, 0.0, 0, None, st)
+    close(dg2, dgo, atol=2e-3, rtol=1e-3)
+    close(db2, dbo, atol=2e-3, rtol=1e-3)
+
+
 def test_scale_dropout_and_mask_bits(be, ob):
     x = g(5, 1000, seed=1)
     for p, site in ((0.2, 1), (0.5, 77), (0.0, 3)):
