@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float), ("out_scale", C.c_float), ("mask_scale", C.c_float),
         ("drop_p", C.c_float),
         ("drop_site", C.c_uint32),
-        ("_pad0", C.c_int32),
+        ("c_zeroed", C.c_int32),
         ("sa_m", C.c_int64), ("sa_k", C.c_int64), ("sa_b1", C.c_int64), ("sa_b2", C.c_int64),
         ("sb_n", C.c_int64), ("sb_k", C.c_int64), ("sb_b1", C.c_int64), ("sb_b2", C.c_int64), ("sb_tap", C.c_int64),
         ("sc_m", C.c_int64), ("sc_n", C.c_int64), ("sc_b1", C.c_int64), ("sc_b2", C.c_int64), ("sc_tap", C.c_int64),

@@ -206,15 +206,21 @@ class CudaBackend:
         self._gemm(d, dy, Bm, dx, None, None, mask, b_off=b_off)
         return dx
 
-    def conv_wgrad(self, dy, x, taps: int):
-        """dW[n,c,tap] = sum_{b,t} dy[b,t,n] x[b,t+tap-pad,c]  -> (N, C, taps) fp32."""
+    def conv_wgrad(self, dy, x, taps: int, out=None, out_zeroed=False):
+        """dW[n,c,tap] = sum_{b,t} dy[b,t,n] x[b,t+tap-pad,c]  -> (N, C, taps) fp32.  `out`: caller-owned
+        destination (e.g. a view of the trainer's flat gradient buffer); `out_zeroed`: it already holds zeros, so a
+        split-K launch needs no clear."""
         Bn, S, N = dy.shape
         Cc = x.shape[-1]
         assert x.shape[:2] == dy.shape[:2] and dy.is_contiguous() and x.is_contiguous()
-        dW = torch.empty(N, Cc, taps, dtype=torch.float32, device=dy.device)
+        if out is None:
+            dW = torch.empty(N, Cc, taps, dtype=torch.float32, device=dy.device)
+        else:
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == N * Cc * taps
+            dW = out.view(N, Cc, taps)
         d = self._desc(N, taps * Cc, Bn * S, GEMM_WGRAD, taps=taps, pad=(taps - 1) // 2, seq=S, cin=Cc,
                        dtype_a=_dt(dy), dtype_b=_dt(x), dtype_c=A3T_F32, sa_k=N, sa_m=1, sb_k=Cc, sb_n=1,
-                       sc_m=Cc * taps, sc_n=taps, sc_tap=1)
+                       sc_m=Cc * taps, sc_n=taps, sc_tap=1, c_zeroed=int(out is not None and out_zeroed))
         self._gemm(d, dy, x, dW)
         return dW
 

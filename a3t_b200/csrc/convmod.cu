@@ -10,6 +10,33 @@ constexpr int DW_MAXK = 32;  // max depthwise kernel size
 constexpr int DW_TPT = 16;   // time steps per thread (256 threads = 64 ch x 4 groups)
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+// bf16 activations: ex2.approx + rcp.approx (a few ulp of fp32, far below one bf16 ulp); the fp32 parity mode keeps expf
+template <typename TU> __device__ __forceinline__ float sigmoid_t(float v) { return sigmoidf_(v); }
+template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+
+// 4 consecutive channels of row `ur` (a at c, gate at C + c) -> GLU values
+template <typename TU>
+__device__ __forceinline__ void load4(const TU* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename TU>
+__device__ __forceinline__ float4 glu4(const TU* ur, int C, int c) {
+  float a[4], g[4];
+  load4<TU>(ur + c, a);
+  load4<TU>(ur + C + c, g);
+  return make_float4(a[0] * sigmoid_t<TU>(g[0]), a[1] * sigmoid_t<TU>(g[1]), a[2] * sigmoid_t<TU>(g[2]),
+                     a[3] * sigmoid_t<TU>(g[3]));
+}
 
 template <typename TU>
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const TU* __restrict__ u, const float* __restrict__ w,
@@ -143,24 +170,17 @@ __global__ void __launch_bounds__(256) glu_dwconv_fwd_kt_kernel(const TU* __rest
                                                                 const float* __restrict__ bias, float* __restrict__ z,
                                                                 int B, int S, int C) {
   constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2;
-  __shared__ float tile[ROWS][DW_TC];
+  __shared__ __align__(16) float tile[ROWS][DW_TC];
   const int ntt = (S + DW_TT - 1) / DW_TT;
   const int b = blockIdx.x / ntt, t0 = (blockIdx.x % ntt) * DW_TT;
   const int c0 = blockIdx.y * DW_TC;
-  // GLU of the haloed tile: 2 channels per thread (bf16x2 / float2 loads)
-  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 2); idx += 256) {
-    int rr = idx / (DW_TC / 2), cc = (idx % (DW_TC / 2)) * 2;
+  // GLU of the haloed tile: 4 channels per thread (8-byte bf16 / 16-byte fp32 loads; C % 4 == 0)
+  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 4); idx += 256) {
+    int rr = idx / (DW_TC / 4), cc = (idx % (DW_TC / 4)) * 4;
     int t = t0 - pad + rr, c = c0 + cc;
-    float v0 = 0.f, v1 = 0.f;
-    if (t >= 0 && t < S && c < C) {
-      const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
-      float a0 = to_f32<TU>(ur[c]), a1 = to_f32<TU>(ur[c + 1]);
-      float g0 = to_f32<TU>(ur[C + c]), g1 = to_f32<TU>(ur[C + c + 1]);
-      v0 = a0 * sigmoidf_(g0);
-      v1 = a1 * sigmoidf_(g1);
-    }
-    tile[rr][cc] = v0;
-    tile[rr][cc + 1] = v1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < S && c < C) v = glu4<TU>(u + ((int64_t)b * S + t) * 2 * C, C, c);
+    *reinterpret_cast<float4*>(&tile[rr][cc]) = v;
   }
   __syncthreads();
   const int cc = threadIdx.x % DW_TC, tg = threadIdx.x / DW_TC;
@@ -188,30 +208,24 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kt_kernel(const float* __r
                                                                 const float* __restrict__ w, TDU* __restrict__ du,
                                                                 float* __restrict__ partial, int B, int S, int C) {
   constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2, padr = KT - 1 - pad;
-  __shared__ float smem_raw[2 * ROWS * DW_TC > 4 * (KT + 1) * DW_TC ? 2 * ROWS * DW_TC : 4 * (KT + 1) * DW_TC];
+  __shared__ __align__(16) float smem_raw[2 * ROWS * DW_TC > 4 * (KT + 1) * DW_TC ? 2 * ROWS * DW_TC : 4 * (KT + 1) * DW_TC];
   float (*tdz)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw);                 // dz, rows from t0-padr
   float (*tgl)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw + ROWS * DW_TC);  // glu, rows from t0-pad
   float (*red)[KT + 1][DW_TC] = reinterpret_cast<float (*)[KT + 1][DW_TC]>(smem_raw);  // reused after sync
   const int ntt = (S + DW_TT - 1) / DW_TT;
   const int b = blockIdx.x / ntt, t0 = (blockIdx.x % ntt) * DW_TT;
   const int c0 = blockIdx.y * DW_TC;
-  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 2); idx += 256) {
-    int rr = idx / (DW_TC / 2), cc = (idx % (DW_TC / 2)) * 2;
+  for (int idx = threadIdx.x; idx < ROWS * (DW_TC / 4); idx += 256) {
+    int rr = idx / (DW_TC / 4), cc = (idx % (DW_TC / 4)) * 4;
     int c = c0 + cc;
     int t = t0 - padr + rr;
-    float2 dv = make_float2(0.f, 0.f);
-    if (t >= 0 && t < S && c < C) dv = *reinterpret_cast<const float2*>(dz + ((int64_t)b * S + t) * C + c);
-    tdz[rr][cc] = dv.x;
-    tdz[rr][cc + 1] = dv.y;
+    float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < S && c < C) dv = *reinterpret_cast<const float4*>(dz + ((int64_t)b * S + t) * C + c);
+    *reinterpret_cast<float4*>(&tdz[rr][cc]) = dv;
     t = t0 - pad + rr;
-    float v0 = 0.f, v1 = 0.f;
-    if (t >= 0 && t < S && c < C) {
-      const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
-      v0 = to_f32<TU>(ur[c]) * sigmoidf_(to_f32<TU>(ur[C + c]));
-      v1 = to_f32<TU>(ur[c + 1]) * sigmoidf_(to_f32<TU>(ur[C + c + 1]));
-    }
-    tgl[rr][cc] = v0;
-    tgl[rr][cc + 1] = v1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < S && c < C) v = glu4<TU>(u + ((int64_t)b * S + t) * 2 * C, C, c);
+    *reinterpret_cast<float4*>(&tgl[rr][cc]) = v;
   }
   __syncthreads();
   const int cc = threadIdx.x % DW_TC, tg = threadIdx.x / DW_TC;
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kt_kernel(const float* __r
         if (t < S) {
           const TU* ur = u + ((int64_t)b * S + t) * 2 * C;
           float a = to_f32<TU>(ur[c]), g = to_f32<TU>(ur[C + c]);
-          float sg = sigmoidf_(g);
+          float sg = sigmoid_t<TU>(g);
           TDU* dur = du + ((int64_t)b * S + t) * 2 * C;
           dur[c] = from_f32<TDU>(dg * sg);
           dur[C + c] = from_f32<TDU>(dg * a * sg * (1.f - sg));
@@ -317,9 +331,9 @@ extern "C" int a3t_glu_dwconv_fwd(const void* u, int dtype_u, const float* w, co
     else                                                                                                        \
       glu_dwconv_fwd_kt_kernel<float, KT><<<grid, 256, 0, st>>>((const float*)u, w, bias, z, B, S, C);          \
   }
-  if (k == 7 && C % 2 == 0) A3T_DW_FWD(7)
-  else if (k == 15 && C % 2 == 0) A3T_DW_FWD(15)
-  else if (k == 31 && C % 2 == 0) A3T_DW_FWD(31)
+  if (k == 7 && C % 4 == 0) A3T_DW_FWD(7)
+  else if (k == 15 && C % 4 == 0) A3T_DW_FWD(15)
+  else if (k == 31 && C % 4 == 0) A3T_DW_FWD(31)
   else if (dtype_u == A3T_BF16)
     glu_dwconv_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)u, w, bias, z, B, S, C, k);
   else
@@ -347,9 +361,9 @@ extern "C" int a3t_glu_dwconv_bwd(const float* dz, const void* u, int dtype_u, c
       glu_dwconv_bwd_kt_kernel<float, float, KT><<<grid, 256, 0, st>>>(dz, (const float*)u, w, (float*)du,      \
                                                                       partial, B, S, C);                        \
   }
-  if (k == 7 && C % 2 == 0) A3T_DW_BWD(7)
-  else if (k == 15 && C % 2 == 0) A3T_DW_BWD(15)
-  else if (k == 31 && C % 2 == 0) A3T_DW_BWD(31)
+  if (k == 7 && C % 4 == 0) A3T_DW_BWD(7)
+  else if (k == 15 && C % 4 == 0) A3T_DW_BWD(15)
+  else if (k == 31 && C % 4 == 0) A3T_DW_BWD(31)
   else if (dtype_u == A3T_BF16)
     glu_dwconv_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
         dz, (const __nv_bfloat16*)u, w, (__nv_bfloat16*)du, partial, B, S, C, k);

@@ -1176,7 +1176,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
     attr_set[cta2 ? 1 : 0][ki] = true;
   }
-  if (p.splits > 1) {
+  if (p.splits > 1 && !d.c_zeroed) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)d.M * d.sc_m * sizeof(float), st);
     if (e != cudaSuccess) {
       set_error("gemm_tc: memset: %s", cudaGetErrorString(e));

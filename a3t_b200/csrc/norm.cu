@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(
 // into partial[blk][2][C]; a second kernel finishes the column sums.
 // ---------------------------------------------------------------------------------------------
 template <typename TDY, int MAXV, typename TG>
-__global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
+__global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_kernel(
     const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ dres, float* __restrict__ dx, float* __restrict__ partial, int64_t rows,
@@ -99,7 +99,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LN_WARPS) {
     const float mean = mean_i[row], rstd = rstd_i[row];
     float xh[MAXV][4], dh[MAXV][4];
+    float4 rres[MAXV];
     float s1 = 0.f, s2 = 0.f;
+    if (dres) {  // issued up front: the loads overlap the statistics instead of following the warp reductions
+#pragma unroll
+      for (int i = 0; i < MAXV; i++) {
+        int c4 = lane + i * 32;
+        if (c4 < nv) rres[i] = __ldcs(reinterpret_cast<const float4*>(dres + row * C) + c4);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < MAXV; i++) {
       int c4 = lane + i * 32;
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_kernel(
         o.z = rstd * (dh[i][2] - s1 - xh[i][2] * s2);
         o.w = rstd * (dh[i][3] - s1 - xh[i][3] * s2);
         if (dres) {
-          float4 r = reinterpret_cast<const float4*>(dres + row * C)[c4];
+          const float4 r = rres[i];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + row * C)[c4] = o;
@@ -697,7 +705,7 @@ extern "C" int a3t_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int a3t_layernorm_bwd_blocks(int64_t rows) {
   int64_t b = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
-  if (b > 148 * 3) b = 148 * 3;
+  if (b > 148 * 2) b = 148 * 2;  // 2 resident blocks per SM (128 registers per thread)
   if (b < 1) b = 1;
   return (int)b;
 }

@@ -122,6 +122,26 @@ def _ffn_fwd(ops, P, wc, pre, norm, x, p_drop, sites, training, ctx):
     return y
 
 
+class _GradOut(dict):
+    """Parameter-gradient dictionary.  `dest` (optional) maps parameter names to caller-owned, ZEROED fp32
+    buffers (the trainer's flat gradient views): weight-gradient GEMMs write straight into them."""
+
+    def __init__(self, P, dest=None):
+        super().__init__()
+        self.P = P
+        self.dest = dest or {}
+
+    def wgrad(self, ops, name, dy, x, taps):
+        """dW of a conv / linear layer from its output gradient dy and input x, in the parameter's own shape."""
+        out = self.dest.get(name)
+        if out is not None:
+            r = ops.conv_wgrad(dy, x, taps, out=out, out_zeroed=True)
+        else:
+            r = ops.conv_wgrad(dy, x, taps)
+        self[name] = r.view(self.P[name].shape)
+        return self[name]
+
+
 def _grad_prep(ops, dy, scale, drop, gpre):
     """g = dropout'(dy * scale) in the GEMM dtype and its column sums: taken from the LayerNorm backward that
     produced dy when it fused them (`gpre`), else computed here."""
@@ -147,11 +167,11 @@ def _ffn_bwd(ops, P, wc, pre, norm, dy, p_drop, training, ctx, G, gpre=None, nxt
     d1, d2 = _drop(p_drop, ctx[f"{ff}.s1"], training), _drop(p_drop, ctx[f"{ff}.s2"], training)
     g, gsum = _grad_prep(ops, dy, 0.5, d2, gpre)
     G[f"{pre}.{ff}.w_2.bias"] = gsum
-    G[f"{pre}.{ff}.w_2.weight"] = ops.conv_wgrad(g, u, w2.taps)
+    G.wgrad(ops, f"{pre}.{ff}.w_2.weight", g, u, w2.taps)
     inv_keep = 1.0 / (1.0 - p_drop) if d1 is not None else 1.0
     du = ops.conv_dgrad(g, w2, mask=u, mask_scale=inv_keep)
     G[f"{pre}.{ff}.w_1.bias"] = ops.colsum(du)
-    G[f"{pre}.{ff}.w_1.weight"] = ops.conv_wgrad(du, h, w1.taps)
+    G.wgrad(ops, f"{pre}.{ff}.w_1.weight", du, h, w1.taps)
     dh = ops.conv_dgrad(du, w1)
     dx, dg, db, gn = _ln_bwd_next(ops, nxt, dh, x, ctx[f"{ff}.mean"], ctx[f"{ff}.rstd"], P[f"{pre}.{norm}.weight"],
                                   P[f"{pre}.{norm}.bias"], dres=dy, eps=1e-12)
@@ -210,7 +230,7 @@ def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G,
     wo = wc.packed(ops, f"{a}.linear_out", [P[f"{a}.linear_out.weight"]], None)
     g, gsum = _grad_prep(ops, dy, 1.0, _drop(p_drop, ctx["mha.s_out"], training), gpre)
     G[f"{a}.linear_out.bias"] = gsum
-    G[f"{a}.linear_out.weight"] = ops.conv_wgrad(g, cx, 1).squeeze(-1)
+    G.wgrad(ops, f"{a}.linear_out.weight", g, cx, 1)
     dcx = ops.conv_dgrad(g, wo)
     dqkv4 = torch.empty_like(qkv4)
     dPd = ops.attn_pv_bwd(dcx, Pd, qkv4, H, dqkv4)
@@ -218,7 +238,7 @@ def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G,
     del dPd
     dpp = ops.attn_scores_bwd(dS, dBD, qkv4, pp, H, dqkv4)
     del dS, dBD
-    G[f"{a}.linear_pos.weight"] = ops.conv_wgrad(ops.cast_act(dpp).unsqueeze(0), pos_d.unsqueeze(0), 1).squeeze(-1)
+    G.wgrad(ops, f"{a}.linear_pos.weight", ops.cast_act(dpp).unsqueeze(0), pos_d.unsqueeze(0), 1)
     db4 = ops.colsum(dqkv4)
     dw4 = ops.conv_wgrad(dqkv4, h, 1).squeeze(-1)
     G[f"{a}.linear_q.weight"] = dw4[0:D] + dw4[D:2 * D]
@@ -261,7 +281,7 @@ def _convmod_bwd(ops, P, wc, pre, dy, p_drop, training, ctx, G, gpre=None, nxt=N
     x, h, u, z, act = ctx["cm.x"], ctx["cm.h"], ctx["cm.u"], ctx["cm.z"], ctx["cm.act"]
     g, gsum = _grad_prep(ops, dy, 1.0, _drop(p_drop, ctx["cm.s"], training), gpre)
     G[f"{c}.pointwise_conv2.bias"] = gsum
-    G[f"{c}.pointwise_conv2.weight"] = ops.conv_wgrad(g, act, 1)
+    G.wgrad(ops, f"{c}.pointwise_conv2.weight", g, act, 1)
     dact = ops.conv_dgrad(g, w2, out_dtype=torch.float32)
     dz, dgam, dbet = ops.bn_act_bwd(dact, z, ctx["cm.bm"], ctx["cm.br"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"],
                                     ACT_SWISH, training, eps=1e-5)
@@ -270,7 +290,7 @@ def _convmod_bwd(ops, P, wc, pre, dy, p_drop, training, ctx, G, gpre=None, nxt=N
     du, dw, db = ops.glu_dwconv_bwd(dz, u, wdw.reshape(wdw.shape[0], wdw.shape[-1]))
     G[f"{c}.depthwise_conv.weight"], G[f"{c}.depthwise_conv.bias"] = dw.reshape(wdw.shape), db
     G[f"{c}.pointwise_conv1.bias"] = ops.colsum(du)
-    G[f"{c}.pointwise_conv1.weight"] = ops.conv_wgrad(du, h, 1)
+    G.wgrad(ops, f"{c}.pointwise_conv1.weight", du, h, 1)
     dh = ops.conv_dgrad(du, w1)
     dx, dg, dbb, gn = _ln_bwd_next(ops, nxt, dh, x, ctx["cm.mean"], ctx["cm.rstd"], P[f"{pre}.norm_conv.weight"],
                                    P[f"{pre}.norm_conv.bias"], dres=dy, eps=1e-12)
@@ -411,11 +431,13 @@ def forward(ops, P: Dict[str, torch.Tensor], wc: WeightCache, cfg: A3TConfig, ba
 
 
 def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: torch.Tensor,
-             dbefore_ext=None, dafter_ext=None) -> Dict[str, torch.Tensor]:
-    """Gradients of all parameters given d loss (and optionally extra grads on before/after)."""
+             dbefore_ext=None, dafter_ext=None, gout=None) -> Dict[str, torch.Tensor]:
+    """Gradients of all parameters given d loss (and optionally extra grads on before/after).
+    gout: optional {parameter name: zeroed fp32 buffer of the parameter's shape}; weight gradients are then
+    written in place (G[name] aliases it) instead of into fresh tensors."""
     sv = ctx.saved
     training = ctx.training
-    G: Dict[str, torch.Tensor] = {}
+    G = _GradOut(P, gout)
     if hasattr(ops, "begin_backward"):
         ops.begin_backward()  # zeroes the arena the small gradient outputs are accumulated into
     speech, masked = sv["speech"], sv["masked"]
@@ -443,14 +465,14 @@ def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: t
             G[f"{bn}.weight"], G[f"{bn}.bias"] = dgam, dbet
             wi = wc.packed(ops, f"postnet.{i}", [P[f"postnet.postnet.{i}.0.weight"]], None)
             dza = ops.cast_act(dz)
-            G[f"postnet.postnet.{i}.0.weight"] = ops.conv_wgrad(dza, e["a_in"], wi.taps)
+            G.wgrad(ops, f"postnet.postnet.{i}.0.weight", dza, e["a_in"], wi.taps)
             d = ops.conv_dgrad(dza, wi, out_dtype=torch.float32)
         dbefore = dbefore + dafter + d
 
     w_sfc = wc.packed(ops, "sfc", [P["sfc.weight"]], None)
     dba = ops.cast_act(dbefore.contiguous())
     G["sfc.bias"] = ops.colsum(dbefore)
-    G["sfc.weight"] = ops.conv_wgrad(dba, sv["zs"], 1).squeeze(-1)
+    G.wgrad(ops, "sfc.weight", dba, sv["zs"], 1)
     dzs = ops.conv_dgrad(dba, w_sfc)
     dz = torch.zeros(Bn, Ts + Tt, D, dtype=dzs.dtype, device=dzs.device)
     dz[:, :Ts] = dzs
@@ -485,7 +507,7 @@ def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: t
     w_in = wc.packed(ops, "enc.prenet", [P["encoder.speech_embed.1.weight"]], None)
     G["encoder.speech_embed.1.bias"] = ops.colsum(dh0)
     dh0a = ops.cast_act(dh0)
-    G["encoder.speech_embed.1.weight"] = ops.conv_wgrad(dh0a, sv["xm"], 1).squeeze(-1)
+    G.wgrad(ops, "encoder.speech_embed.1.weight", dh0a, sv["xm"], 1)
     dxm = ops.conv_dgrad(dh0a, w_in, out_dtype=torch.float32)
     G["encoder.speech_embed.0.mask_feature"] = ops.mask_input_bwd(dxm, masked).reshape(1, 1, -1)
     return G

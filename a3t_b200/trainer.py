@@ -70,8 +70,12 @@ class DataParallelTrainer:
         B = batch["speech"].shape[0]
         loss, before, after, ctx = graph.forward(ops, P, wc, cfg, batch, True, True)
         gloss = torch.full((1,), float(B), dtype=torch.float32, device=self.device)
-        G = graph.backward(ops, P, wc, cfg, ctx, gloss)
-        torch._foreach_copy_([self.gviews[n] for n in self.names], [G[n].view(self.gviews[n].shape) for n in self.names])
+        # one clear of the flat gradient buffer: weight-gradient GEMMs then write (split-K: accumulate) straight
+        # into its views; only the small vectors (biases, norms, embeddings) are copied in afterwards
+        self.flat_g.zero_()
+        G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews)
+        rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
+        torch._foreach_copy_([self.gviews[n] for n in rest], [G[n].view(self.gviews[n].shape) for n in rest])
         self.stats[0:1].copy_(loss).mul_(float(B))
         self.stats[1:2].copy_(loss).mul_(float(B))
         self.stats[2:3].fill_(float(B))

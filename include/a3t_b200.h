@@ -79,7 +79,8 @@ typedef struct A3tGemmDesc {
   float alpha, out_scale, mask_scale;
   float drop_p;
   uint32_t drop_site;
-  int32_t _pad0;
+  int32_t c_zeroed; /* 1: C already holds zeros (or a value to accumulate into): a split-K WGRAD adds its partial
+                     * sums without clearing C first; 0: the library clears C itself when it splits K */
   int64_t sa_m, sa_k, sa_b1, sa_b2;
   int64_t sb_n, sb_k, sb_b1, sb_b2, sb_tap;
   int64_t sc_m, sc_n, sc_b1, sc_b2, sc_tap;
