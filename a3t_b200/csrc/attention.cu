@@ -2,6 +2,7 @@
 // (transformer/attention.py:145-165 rel_shift, :205-207 scale, :79-88 mask/softmax/zero/dropout).
 // One warp per (b,h,i) score row; the row lives in shared memory.
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace a3t {
@@ -254,6 +255,200 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// bf16 register-resident kernels (the tensor-core mode's score tensors), S % 4 == 0, S <= 128 * NIT.
+// A warp owns a row; every lane issues ALL of the row's loads before the first use (the v4 kernels above
+// stage the row in shared memory and wait on each 8-byte load in turn: they are latency- and
+// instruction-bound at ~40 % of HBM bandwidth).  rel_shift as a contiguous slice: with G = BD_raw[b,h]
+// flattened, shifted[i, j] = G[o + j] (j <= i), 0 (j == i+1), G[o + j - 1] (j >= i+2), o = (i+1)(S-1)
+// (transformer/attention.py:155-159).  A lane's 4 keys therefore sit in ONE 16-byte aligned-pair window of
+// G: two aligned 8-byte loads and a funnel shift replace four 2-byte loads with per-element branches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bf16x4_to_f32(uint32_t w0, uint32_t w1, float (&v)[4]) {
+  v[0] = __uint_as_float(w0 << 16); v[1] = __uint_as_float(w0 & 0xFFFF0000u);
+  v[2] = __uint_as_float(w1 << 16); v[3] = __uint_as_float(w1 & 0xFFFF0000u);
+}
+// element `idx` (0..7) of the 8 bf16 held in words w[0..3]
+__device__ __forceinline__ float bf16_at(const uint32_t (&w)[4], int idx) {
+  const uint32_t word = idx < 4 ? (idx < 2 ? w[0] : w[1]) : (idx < 6 ? w[2] : w[3]);
+  return __uint_as_float((idx & 1) ? (word & 0xFFFF0000u) : (word << 16));
+}
+
+template <int NIT>
+__global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_kernel(
+    const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
+    __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    const unsigned long long* __restrict__ seed, uint32_t site) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Drop dr = make_drop(drop_p, seed, site);
+  const int64_t nrows = (int64_t)B * H * S;
+  const int64_t SS = (int64_t)S * S;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < nrows; r += (int64_t)gridDim.x * 8) {
+    const int i = (int)(r % S);
+    const int64_t bh = r / S;
+    const int b = (int)(bh / H);
+    const __nv_bfloat16* acr = ac + r * S;
+    const __nv_bfloat16* G = bd_raw + bh * SS;
+    const uint8_t* km = keymask + (int64_t)b * S;
+    const int64_t o = (int64_t)(i + 1) * (S - 1);
+    uint2 a[NIT], w01[NIT], w23[NIT];
+    uchar4 k4[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        a[it] = __ldcs(reinterpret_cast<const uint2*>(acr + j));
+        k4[it] = *reinterpret_cast<const uchar4*>(km + j);
+        // window base: G index of key j (rows fully left of the gap) or of key j-1 (everything else)
+        const int64_t x = o + j - ((j + 3 <= i) ? 0 : 1);
+        const int64_t x4 = x & ~(int64_t)3;
+        w01[it] = __ldcs(reinterpret_cast<const uint2*>(G + x4));
+        w23[it] = (x4 + 8 <= SS) ? __ldcs(reinterpret_cast<const uint2*>(G + x4 + 4)) : make_uint2(0u, 0u);
+      }
+    }
+    float v[NIT][4];
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        float av[4], bv[4];
+        bf16x4_to_f32(a[it].x, a[it].y, av);
+        const bool left = j + 3 <= i, right = j >= i + 2;
+        const int d = (int)((o + j - (left ? 0 : 1)) & 3);
+        const uint32_t w[4] = {w01[it].x, w01[it].y, w23[it].x, w23[it].y};
+        if (left || right) {  // 4 consecutive elements of G starting d elements into the window
+          const uint32_t sh = (d & 1) * 16;
+          const uint32_t q0 = (d & 2) ? w[1] : w[0], q1 = (d & 2) ? w[2] : w[1], q2 = (d & 2) ? w[3] : w[2];
+          bf16x4_to_f32(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), bv);
+        } else {              // the group holding the zero at j == i+1 (window based at key j-1)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int jj = j + e;
+            bv[e] = jj == i + 1 ? 0.f : bf16_at(w, d + (jj <= i ? e + 1 : e));
+          }
+        }
+        const unsigned char kk[4] = {k4[it].x, k4[it].y, k4[it].z, k4[it].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float t = (av[e] + bv[e]) * scale;
+          if (!kk[e]) t = -FLT_MAX;  // finfo(float32).min
+          v[it][e] = t;
+          mx = fmaxf(mx, t);
+        }
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      if (lane * 4 + it * 128 < S) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          v[it][e] = __expf(v[it][e] - mx);
+          sum += v[it][e];
+        }
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        const unsigned char kk[4] = {k4[it].x, k4[it].y, k4[it].z, k4[it].w};
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) pv[e] = kk[e] ? v[it][e] * inv : 0.f;
+        store_p4<__nv_bfloat16>(P + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+        if (dr.on) {
+          bool kp[4];
+          drop_keep4(dr, drop_fold((unsigned long long)(r * S + j)), kp);
+#pragma unroll
+          for (int e = 0; e < 4; e++) pv[e] = kp[e] ? pv[e] * dr.inv_keep : 0.f;
+          store_p4<__nv_bfloat16>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+        } else if (Pd != P) {
+          store_p4<__nv_bfloat16>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+        }
+      }
+    }
+  }
+}
+
+template <int NIT>
+__global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_kernel(
+    const __nv_bfloat16* __restrict__ dPd, const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dS,
+    __nv_bfloat16* __restrict__ dBD, int64_t nrows, int S, float scale, float drop_p,
+    const unsigned long long* __restrict__ seed, uint32_t site) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Drop dr = make_drop(drop_p, seed, site);
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < nrows; r += (int64_t)gridDim.x * 8) {
+    const int i = (int)(r % S);
+    uint2 gw[NIT], pw[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        gw[it] = __ldcs(reinterpret_cast<const uint2*>(dPd + r * S + j));
+        pw[it] = __ldcs(reinterpret_cast<const uint2*>(P + r * S + j));
+      }
+    }
+    float g[NIT][4];
+    float dot = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        float pv[4];
+        bf16x4_to_f32(gw[it].x, gw[it].y, g[it]);
+        bf16x4_to_f32(pw[it].x, pw[it].y, pv);
+        if (dr.on) {
+          bool kp[4];
+          drop_keep4(dr, drop_fold((unsigned long long)(r * S + j)), kp);
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[it][e] = kp[e] ? g[it][e] * dr.inv_keep : 0.f;
+        }
+        dot += (g[it][0] * pv[0] + g[it][1] * pv[1]) + (g[it][2] * pv[2] + g[it][3] * pv[3]);
+      }
+    }
+    dot = warp_sum(dot);
+    // inverse rel_shift: row i of dS is the contiguous run dBD_flat[o .. o+S-2] (matrix-local) with key i+1 dropped
+    __nv_bfloat16* const run = dBD + (r - i) * S + (int64_t)(i + 1) * (S - 1);
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int j = lane * 4 + it * 128;
+      if (j < S) {
+        float pv[4];
+        bf16x4_to_f32(pw[it].x, pw[it].y, pv);
+        __nv_bfloat162 h[2] = {__floats2bfloat162_rn(pv[0] * (g[it][0] - dot) * scale, pv[1] * (g[it][1] - dot) * scale),
+                               __floats2bfloat162_rn(pv[2] * (g[it][2] - dot) * scale, pv[3] * (g[it][3] - dot) * scale)};
+        *reinterpret_cast<uint2*>(dS + r * S + j) = *reinterpret_cast<const uint2*>(h);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(h);
+        if (j + 3 <= i) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) run[j + e] = hv[e];
+        } else if (j >= i + 2) {
+          if (i + 1 < S) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) run[j + e - 1] = hv[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int jj = j + e;
+            if (jj <= i) run[jj] = hv[e];
+            else if (jj >= i + 2 && i + 1 < S) run[jj - 1] = hv[e];
+          }
+        }
+      }
+    }
+    if (i == 0) {  // BD_raw[0, 0..S-2] is never read by the forward
+      for (int j = lane; j < S - 1; j += 32) dBD[r * S + j] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
 }  // namespace a3t
 
 using namespace a3t;
@@ -271,6 +466,19 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
   const bool v4 = (S % 4) == 0 && ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
+  if (v4 && dtype_p == A3T_BF16 && dtype_in == A3T_BF16 && S <= 2048 && (((uintptr_t)bd_raw & 15) == 0) &&
+      !getenv("A3T_SOFTMAX_SMEM")) {
+    int rb = (int)((nrows + 7) / 8);
+    if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
+#define A3T_SM_FWD_REG(NIT)                                                                               \
+  relpos_softmax_fwd_reg_kernel<NIT><<<rb, 256, 0, st>>>((const __nv_bfloat16*)ac, (const __nv_bfloat16*)bd_raw, keymask, \
+                                                         (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p,  \
+                                                         seed, site)
+    if (S <= 128 * 5) A3T_SM_FWD_REG(5);
+    else if (S <= 128 * 9) A3T_SM_FWD_REG(9);
+    else A3T_SM_FWD_REG(16);
+    return check_launch("relpos_softmax_fwd");
+  }
   if (v4 && smem <= 48 * 1024) {
 #define A3T_SM_FWD(TPT, TIT)                                                                              \
   relpos_softmax_fwd_v4_kernel<TPT, TIT><<<blocks, SM_WARPS * 32, smem, st>>>(                            \
@@ -332,6 +540,20 @@ extern "C" int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void*
   A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_bwd: S=%d out of range", S);
   A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_bwd: bad input dtype");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_in == A3T_BF16 && dtype_p == A3T_BF16 && dtype_o == A3T_BF16 && (S % 4) == 0 && S <= 2048 &&
+      ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0) && !getenv("A3T_SOFTMAX_SMEM")) {
+    const int64_t nrows = (int64_t)B * H * S;
+    int rb = (int)((nrows + 7) / 8);
+    if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
+#define A3T_SM_BWD_REG(NIT)                                                                                      \
+  relpos_softmax_bwd_reg_kernel<NIT><<<rb, 256, 0, st>>>((const __nv_bfloat16*)dPd, (const __nv_bfloat16*)P,        \
+                                                         (__nv_bfloat16*)dS, (__nv_bfloat16*)dBD, nrows, S, scale, \
+                                                         drop_p, seed, site)
+    if (S <= 128 * 5) A3T_SM_BWD_REG(5);
+    else if (S <= 128 * 9) A3T_SM_BWD_REG(9);
+    else A3T_SM_BWD_REG(16);
+    return check_launch("relpos_softmax_bwd");
+  }
   if (dtype_p == A3T_BF16 && dtype_o == A3T_BF16)
     return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
   if (dtype_p == A3T_F32 && dtype_o == A3T_F32)

@@ -180,6 +180,39 @@ def test_attention(be, ob, B, H, S, dk):
         close(dq_c, dq_o)
 
 
+@pytest.mark.parametrize("B,H,S", [(2, 2, 1152), (1, 2, 260), (1, 1, 1692), (2, 1, 128)])
+def test_relpos_softmax_bf16_register_kernels(cuda_lib, ob, B, H, S):
+    """The tensor-core mode's bf16 softmax kernels (row in registers, rel_shift through aligned window loads)
+    against the oracle on the same bf16-rounded inputs: P within one bf16 ulp, identical dropout pattern,
+    and dBD_raw = the EXACT inverse rel_shift of the kernel's own dS (a pure index map: bit-exact)."""
+    from a3t_b200.backend import CudaBackend
+
+    bb = CudaBackend("cuda:0", torch.bfloat16, seed=987654321)
+    obb = OracleBackend(seed=987654321)
+    ac = g(B, H, S, S, seed=1, scale=2.0).to(torch.bfloat16)
+    bd = g(B, H, S, S, seed=2, scale=2.0).to(torch.bfloat16)
+    keymask = torch.ones(B, S, dtype=torch.bool)
+    keymask[0, S - 5:] = False
+    sc = 0.125
+    for dr in (None, (0.2, 6)):
+        Po, Pdo = obb.relpos_softmax_fwd(ac.float(), bd.float(), keymask, sc, drop=dr)
+        Pc, Pdc = bb.relpos_softmax_fwd(ac.cuda(), bd.cuda(), keymask.cuda(), sc, drop=dr)
+        assert Pc.dtype == torch.bfloat16
+        close(Pc, Po, atol=1e-6, rtol=1e-2)
+        close(Pdc, Pdo, atol=1e-6, rtol=1e-2)
+        if dr is not None:
+            assert torch.equal((Pdc.cpu() == 0) & (Pc.cpu() != 0), (Pdo == 0) & (Pc.cpu() != 0))
+        assert float(Pc[0, :, :, S - 5:].abs().max()) == 0.0
+        dP = g(B, H, S, S, seed=3).to(torch.bfloat16)
+        dSo, _ = obb.relpos_softmax_bwd(dP.float(), Pc.float().cpu(), sc, drop=dr)
+        dSc, dBc = bb.relpos_softmax_bwd(dP.cuda(), Pc, sc, drop=dr)
+        close(dSc, dSo, atol=2e-3 * float(dSo.abs().max()), rtol=2e-2)
+        # inverse rel_shift of the kernel's own dS: the vjp of the oracle's rel_shift is a pure scatter
+        x = torch.zeros(B, H, S, S, requires_grad=True)
+        O.rel_shift(x).backward(dSc.float().cpu())
+        assert torch.equal(dBc.float().cpu(), x.grad)
+
+
 def test_rel_shift_index_map_is_exact(be):
     """BD' = rel_shift(BD) must be an exact gather (no arithmetic): feed integers, AC = 0, and
     compare the pre-softmax ordering through a one-hot trick."""
