@@ -275,108 +275,131 @@ __device__ __forceinline__ float bf16_at(const uint32_t (&w)[4], int idx) {
   return __uint_as_float((idx & 1) ? (word & 0xFFFF0000u) : (word << 16));
 }
 
-template <int NIT>
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NIT, bool FULL>  // FULL: S == 128 * NIT, no tail guards
 __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_kernel(
     const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
     __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
-    const unsigned long long* __restrict__ seed, uint32_t site) {
+    const unsigned long long* __restrict__ seed, uint32_t site, int dbg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Drop dr = make_drop(drop_p, seed, site);
   const int64_t nrows = (int64_t)B * H * S;
-  const int64_t SS = (int64_t)S * S;
+  const int SS = S * S;  // S <= 2048
+  const float c2 = scale * 1.4426950408889634f;  // softmax in base 2: exp(s - m) = 2^((s - m) log2 e)
   for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < nrows; r += (int64_t)gridDim.x * 8) {
     const int i = (int)(r % S);
     const int64_t bh = r / S;
     const int b = (int)(bh / H);
     const __nv_bfloat16* acr = ac + r * S;
+    __nv_bfloat16* const Pr = P + r * S;
+    __nv_bfloat16* const Pdr = Pd + r * S;
+    const unsigned long long ebase = (unsigned long long)(r * S);
     const __nv_bfloat16* G = bd_raw + bh * SS;
     const uint8_t* km = keymask + (int64_t)b * S;
-    const int64_t o = (int64_t)(i + 1) * (S - 1);
+    // windows: groups left of the gap start at G[o + j], all others at G[o + j - 1]; 8-byte aligned bases
+    const int o = (i + 1) * (S - 1);
+    const int basel = o & ~3, baser = (o - 1) & ~3;
+    const int dl = o & 3, dg = (o - 1) & 3;
     uint2 a[NIT], w01[NIT], w23[NIT];
-    uchar4 k4[NIT];
+    uint32_t kw[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
-      const int j = lane * 4 + it * 128;
-      if (j < S) {
-        a[it] = __ldcs(reinterpret_cast<const uint2*>(acr + j));
-        k4[it] = *reinterpret_cast<const uchar4*>(km + j);
-        // window base: G index of key j (rows fully left of the gap) or of key j-1 (everything else)
-        const int64_t x = o + j - ((j + 3 <= i) ? 0 : 1);
-        const int64_t x4 = x & ~(int64_t)3;
-        w01[it] = __ldcs(reinterpret_cast<const uint2*>(G + x4));
-        w23[it] = (x4 + 8 <= SS) ? __ldcs(reinterpret_cast<const uint2*>(G + x4 + 4)) : make_uint2(0u, 0u);
+      // groups past the end of the row (S < 128 * NIT) re-load the last group: no branch in the load phase,
+      // their scores are forced to -inf below and their stores are skipped
+      const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
+      {
+        a[it] = (dbg & 4) ? make_uint2(0u, 0u) : __ldcs(reinterpret_cast<const uint2*>(acr + j));
+        const int x4 = ((j + 3 <= i) ? basel : baser) + j;
+        w01[it] = (dbg & 1) ? make_uint2(0u, 0u) : __ldg(reinterpret_cast<const uint2*>(G + x4));
+        w23[it] = (x4 + 8 <= SS && !(dbg & 1)) ? __ldg(reinterpret_cast<const uint2*>(G + x4 + 4)) : make_uint2(0u, 0u);
+        kw[it] = *reinterpret_cast<const uint32_t*>(km + j);  // consumed only after every load is in flight
       }
     }
+    uint32_t notall = 0;  // bit it: some key of the group is padded
+#pragma unroll
+    for (int it = 0; it < NIT; it++)
+      if (kw[it] != 0x01010101u) notall |= 1u << it;
     float v[NIT][4];
     float mx = -FLT_MAX;
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
-      const int j = lane * 4 + it * 128;
-      if (j < S) {
+      const bool ok = FULL || lane * 4 + it * 128 < S;
+      const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
+      {
         float av[4], bv[4];
         bf16x4_to_f32(a[it].x, a[it].y, av);
-        const bool left = j + 3 <= i, right = j >= i + 2;
-        const int d = (int)((o + j - (left ? 0 : 1)) & 3);
-        const uint32_t w[4] = {w01[it].x, w01[it].y, w23[it].x, w23[it].y};
-        if (left || right) {  // 4 consecutive elements of G starting d elements into the window
+        const bool left = j + 3 <= i;
+        const int d = left ? dl : dg;
+        if (left || j >= i + 2) {  // 4 consecutive elements of G, d elements into the window
           const uint32_t sh = (d & 1) * 16;
-          const uint32_t q0 = (d & 2) ? w[1] : w[0], q1 = (d & 2) ? w[2] : w[1], q2 = (d & 2) ? w[3] : w[2];
+          const bool hi = (d & 2) != 0;
+          const uint32_t q0 = hi ? w01[it].y : w01[it].x, q1 = hi ? w23[it].x : w01[it].y, q2 = hi ? w23[it].y : w23[it].x;
           bf16x4_to_f32(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), bv);
-        } else {              // the group holding the zero at j == i+1 (window based at key j-1)
+        } else {                   // the one group per row that holds the zero at key i+1
+          const uint32_t w[4] = {w01[it].x, w01[it].y, w23[it].x, w23[it].y};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const int jj = j + e;
             bv[e] = jj == i + 1 ? 0.f : bf16_at(w, d + (jj <= i ? e + 1 : e));
           }
         }
-        const unsigned char kk[4] = {k4[it].x, k4[it].y, k4[it].z, k4[it].w};
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float t = (av[e] + bv[e]) * scale;
-          if (!kk[e]) t = -FLT_MAX;  // finfo(float32).min
-          v[it][e] = t;
-          mx = fmaxf(mx, t);
+        for (int e = 0; e < 4; e++) v[it][e] = (av[e] + bv[e]) * c2;
+        if (notall & (1u << it)) {
+          const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
+          if (!k4.x) v[it][0] = -FLT_MAX;  // finfo(float32).min
+          if (!k4.y) v[it][1] = -FLT_MAX;
+          if (!k4.z) v[it][2] = -FLT_MAX;
+          if (!k4.w) v[it][3] = -FLT_MAX;
         }
+        if (!ok) v[it][0] = v[it][1] = v[it][2] = v[it][3] = -FLT_MAX;  // duplicate of the last group: exp -> 0
+        mx = fmaxf(mx, fmaxf(fmaxf(v[it][0], v[it][1]), fmaxf(v[it][2], v[it][3])));
       }
     }
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
-      if (lane * 4 + it * 128 < S) {
+      {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          v[it][e] = __expf(v[it][e] - mx);
-          sum += v[it][e];
-        }
+        for (int e = 0; e < 4; e++) v[it][e] = (dbg & 2) ? v[it][e] - mx : ex2_approx(v[it][e] - mx);
+        sum += (v[it][0] + v[it][1]) + (v[it][2] + v[it][3]);
       }
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
+    const float inv_dk = inv * dr.inv_keep;
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
       const int j = lane * 4 + it * 128;
-      if (j < S) {
-        const unsigned char kk[4] = {k4[it].x, k4[it].y, k4[it].z, k4[it].w};
-        float pv[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) pv[e] = kk[e] ? v[it][e] * inv : 0.f;
-        store_p4<__nv_bfloat16>(P + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+      if (FULL || j < S) {
+        if (notall & (1u << it)) {  // padded keys get probability 0 (attention.py:86)
+          const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
+          if (!k4.x) v[it][0] = 0.f;
+          if (!k4.y) v[it][1] = 0.f;
+          if (!k4.z) v[it][2] = 0.f;
+          if (!k4.w) v[it][3] = 0.f;
+        }
+        store_p4<__nv_bfloat16>(Pr + j, v[it][0] * inv, v[it][1] * inv, v[it][2] * inv, v[it][3] * inv);
         if (dr.on) {
           bool kp[4];
-          drop_keep4(dr, drop_fold((unsigned long long)(r * S + j)), kp);
-#pragma unroll
-          for (int e = 0; e < 4; e++) pv[e] = kp[e] ? pv[e] * dr.inv_keep : 0.f;
-          store_p4<__nv_bfloat16>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+          drop_keep4(dr, drop_fold(ebase + (unsigned long long)j), kp);
+          store_p4<__nv_bfloat16>(Pdr + j, kp[0] ? v[it][0] * inv_dk : 0.f, kp[1] ? v[it][1] * inv_dk : 0.f,
+                                  kp[2] ? v[it][2] * inv_dk : 0.f, kp[3] ? v[it][3] * inv_dk : 0.f);
         } else if (Pd != P) {
-          store_p4<__nv_bfloat16>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+          store_p4<__nv_bfloat16>(Pdr + j, v[it][0] * inv, v[it][1] * inv, v[it][2] * inv, v[it][3] * inv);
         }
       }
     }
   }
 }
 
-template <int NIT>
+template <int NIT, bool FULL>
 __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_kernel(
     const __nv_bfloat16* __restrict__ dPd, const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dS,
     __nv_bfloat16* __restrict__ dBD, int64_t nrows, int S, float scale, float drop_p,
@@ -388,18 +411,18 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
     uint2 gw[NIT], pw[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
-      const int j = lane * 4 + it * 128;
-      if (j < S) {
-        gw[it] = __ldcs(reinterpret_cast<const uint2*>(dPd + r * S + j));
-        pw[it] = __ldcs(reinterpret_cast<const uint2*>(P + r * S + j));
-      }
+      // groups past the end of the row re-load the last group (no branch in the load phase); they are zeroed below
+      const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
+      gw[it] = __ldcs(reinterpret_cast<const uint2*>(dPd + r * S + j));
+      pw[it] = __ldcs(reinterpret_cast<const uint2*>(P + r * S + j));
+      if (!FULL && lane * 4 + it * 128 >= S) pw[it] = make_uint2(0u, 0u);
     }
     float g[NIT][4];
     float dot = 0.f;
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
-      const int j = lane * 4 + it * 128;
-      if (j < S) {
+      const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
+      {
         float pv[4];
         bf16x4_to_f32(gw[it].x, gw[it].y, g[it]);
         bf16x4_to_f32(pw[it].x, pw[it].y, pv);
@@ -418,7 +441,7 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
       const int j = lane * 4 + it * 128;
-      if (j < S) {
+      if (FULL || j < S) {
         float pv[4];
         bf16x4_to_f32(pw[it].x, pw[it].y, pv);
         __nv_bfloat162 h[2] = {__floats2bfloat162_rn(pv[0] * (g[it][0] - dot) * scale, pv[1] * (g[it][1] - dot) * scale),
@@ -470,13 +493,14 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
       !getenv("A3T_SOFTMAX_SMEM")) {
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
-#define A3T_SM_FWD_REG(NIT)                                                                               \
-  relpos_softmax_fwd_reg_kernel<NIT><<<rb, 256, 0, st>>>((const __nv_bfloat16*)ac, (const __nv_bfloat16*)bd_raw, keymask, \
+#define A3T_SM_FWD_REG(NIT, FULL)                                                                               \
+  relpos_softmax_fwd_reg_kernel<NIT, FULL><<<rb, 256, 0, st>>>((const __nv_bfloat16*)ac, (const __nv_bfloat16*)bd_raw, keymask, \
                                                          (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p,  \
-                                                         seed, site)
-    if (S <= 128 * 5) A3T_SM_FWD_REG(5);
-    else if (S <= 128 * 9) A3T_SM_FWD_REG(9);
-    else A3T_SM_FWD_REG(16);
+                                                         seed, site, getenv("A3T_SM_DBG") ? atoi(getenv("A3T_SM_DBG")) : 0)
+    if (S == 128 * 9) A3T_SM_FWD_REG(9, true);
+    else if (S <= 128 * 5) A3T_SM_FWD_REG(5, false);
+    else if (S <= 128 * 9) A3T_SM_FWD_REG(9, false);
+    else A3T_SM_FWD_REG(16, false);
     return check_launch("relpos_softmax_fwd");
   }
   if (v4 && smem <= 48 * 1024) {
@@ -545,13 +569,14 @@ extern "C" int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void*
     const int64_t nrows = (int64_t)B * H * S;
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
-#define A3T_SM_BWD_REG(NIT)                                                                                      \
-  relpos_softmax_bwd_reg_kernel<NIT><<<rb, 256, 0, st>>>((const __nv_bfloat16*)dPd, (const __nv_bfloat16*)P,        \
+#define A3T_SM_BWD_REG(NIT, FULL)                                                                                      \
+  relpos_softmax_bwd_reg_kernel<NIT, FULL><<<rb, 256, 0, st>>>((const __nv_bfloat16*)dPd, (const __nv_bfloat16*)P,        \
                                                          (__nv_bfloat16*)dS, (__nv_bfloat16*)dBD, nrows, S, scale, \
                                                          drop_p, seed, site)
-    if (S <= 128 * 5) A3T_SM_BWD_REG(5);
-    else if (S <= 128 * 9) A3T_SM_BWD_REG(9);
-    else A3T_SM_BWD_REG(16);
+    if (S == 128 * 9) A3T_SM_BWD_REG(9, true);
+    else if (S <= 128 * 5) A3T_SM_BWD_REG(5, false);
+    else if (S <= 128 * 9) A3T_SM_BWD_REG(9, false);
+    else A3T_SM_BWD_REG(16, false);
     return check_launch("relpos_softmax_bwd");
   }
   if (dtype_p == A3T_BF16 && dtype_o == A3T_BF16)
