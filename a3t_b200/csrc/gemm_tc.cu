@@ -361,7 +361,8 @@ constexpr int EPI_WGRAD_TMA = 17;  // fp32 weight gradient through TMA tensor st
 template <int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -381,11 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * MAX_STAGES + 5 + w); };  // one per epilogue warp
 
   if (warp == PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     if constexpr (EPI >= 0 && EPI != EPI_WGRAD) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
+    if constexpr (EPI >= 0 && EPI < 16 && (EPI & 4)) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
     for (int s = 0; s < p.stages; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -394,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), NUM_EPI_WARPS * per_unit);  // pair mode: the peer's epilogue warps arrive remotely
     }
+    for (int w = 0; w < NUM_EPI_WARPS; w++) mbar_init(res_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -709,6 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nsc = (dbg >= 5) ? 0 : (p.block_n + SC_COLS - 1) / SC_COLS;
       const uint32_t stg_row = stg + lane * 128;
       const uint32_t sw = (uint32_t)(lane & 7);
+      uint32_t rph = 0;  // phase of this warp's residual barrier
       for (int w = group; w < p.num_work; w += ngroups) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
         const int trow0 = t.m0 + q * 32;                              // first row of this warp (in sequence / matrix)
@@ -716,20 +721,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int mrow = (d.mode == A3T_GEMM_CONV) ? t.seq_idx * d.seq + row : row;  // row inside C
         const bool row_ok = row < row_lim && (d.mode != A3T_GEMM_CONV || t.seq_idx * d.seq < d.M);
         const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2 + (int64_t)mrow * d.sc_m;
-        const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2 + (int64_t)mrow * d.sr_m;
         const unsigned long long dbase = ((unsigned long long)t.z * d.M + mrow) * (unsigned long long)d.N;
         const int cc2 = (d.mode == A3T_GEMM_CONV) ? t.seq_idx : t.b2, cc3 = (d.mode == A3T_GEMM_CONV) ? 0 : t.b1;
         bool waited = false, released = false;
         for (int sc = half; sc < nsc; sc += NUM_EPI_WARPS / 4) {
           const int n0c = t.n0 + sc * SC_COLS;
           // operands of the epilogue that live in global memory: issue the loads before waiting on TMEM
-          float4 rv[kRes ? SC_COLS / 4 : 1];
           uint4 mk[kMask ? SC_COLS / 8 : 1];
           if constexpr (kRes) {
-#pragma unroll
-            for (int g4 = 0; g4 < SC_COLS / 4; g4++) {
-              rv[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row_ok && n0c + 4 * g4 < d.N) rv[g4] = __ldg((const float4*)(p.res + rbase + n0c + 4 * g4));
+            // residual tile (32 rows x 128 B, fp32): TMA-loaded into this warp's staging buffer while the
+            // accumulator is read and the bias / dropout math runs; added in place before the tensor store
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has read the buffer
+              mbar_expect_tx(res_bar(ew), 32 * 128);
+              tma_load_4d(stg, &tmR, res_bar(ew), n0c, trow0, cc2, cc3);
             }
           }
           if constexpr (kMask) {
@@ -785,9 +790,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 4; j++) v[j] *= out_scale;
             }
-            if constexpr (kRes) {
-              v[0] += rv[g4].x; v[1] += rv[g4].y; v[2] += rv[g4].z; v[3] += rv[g4].w;
-            }
             if constexpr (kBf16) {
               __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
               acc[2 * g4] = *reinterpret_cast<uint32_t*>(&h0);       // packed in place: unit u = acc[4u .. 4u+3]
@@ -797,9 +799,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 4; j++) acc[4 * g4 + j] = __float_as_uint(v[j]);
             }
           }
-          // the previous TMA store of this warp must have finished READING the staging rows
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
+          if constexpr (kRes) {
+            mbar_wait(res_bar(ew), rph);  // residual rows have landed (rows / columns outside the tensor read as 0)
+            rph ^= 1u;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              float4 rr;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                           : "r"(stg_row + ((u ^ sw) << 4))
+                           : "memory");
+              acc[4 * u] = __float_as_uint(__uint_as_float(acc[4 * u]) + rr.x);
+              acc[4 * u + 1] = __float_as_uint(__uint_as_float(acc[4 * u + 1]) + rr.y);
+              acc[4 * u + 2] = __float_as_uint(__uint_as_float(acc[4 * u + 2]) + rr.z);
+              acc[4 * u + 3] = __float_as_uint(__uint_as_float(acc[4 * u + 3]) + rr.w);
+            }
+          } else {
+            // the previous TMA store of this warp must have finished READING the staging rows
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
 #pragma unroll
           for (int u = 0; u < 8; u++)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ sw) << 4)), "r"(acc[4 * u]),
@@ -1098,7 +1117,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   abox[1] = p.a_mn ? BLOCK_K : BLOCK_M;
   bbox[1] = p.b_mn ? BLOCK_K : b_rows;
   const uint32_t stage_bytes = A_STAGE_BYTES + b_rows * BLOCK_K * 2;
-  const int bar_bytes = 8 * (2 * MAX_STAGES + 4) + 16;
+  const int bar_bytes = 8 * (2 * MAX_STAGES + 5 + NUM_EPI_WARPS) + 16;
   const int epi_bytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
   p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes - epi_bytes) / (int)stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -1126,7 +1145,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
 
   // ---- epilogue class -------------------------------------------------------------------------
   int epi = -1;
-  CUtensorMap tmC = tmA;  // placeholder unless the TMA-store epilogue is selected
+  CUtensorMap tmC = tmA, tmR = tmA;  // placeholders unless the TMA epilogue is selected
   if (wg_tma) {
     int64_t cdims[4] = {(int64_t)d.cin * d.taps, d.M, 1, 1}, cstr[3] = {d.sc_m, d.sc_m, d.sc_m};
     int cbox[4] = {32, 32, 1, 1};
@@ -1153,12 +1172,20 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
       }
       bool ok = true;
       for (int i = 0; i < 3; i++) ok = ok && cstr[i] > 0 && cstr[i] < ((int64_t)1 << 37) && ((cstr[i] * cs) % 16) == 0;
+      if (ok && res) {  // residual: same coordinates as C, its own strides (fp32)
+        int64_t rstr[3];
+        rstr[0] = d.sr_m;
+        if (d.mode == A3T_GEMM_CONV) { rstr[1] = (int64_t)d.seq * d.sr_m; rstr[2] = rstr[1]; }
+        else { rstr[1] = d.batch2 > 1 ? d.sr_b2 : d.sr_m; rstr[2] = d.batch1 > 1 ? d.sr_b1 : d.sr_m; }
+        for (int i = 0; i < 3; i++) ok = ok && rstr[i] > 0 && rstr[i] < ((int64_t)1 << 37) && ((rstr[i] * 4) % 16) == 0;
+        ok = ok && encode_map(&tmR, res, cdims, rstr, cbox, 4);
+      }
       if (ok && encode_map(&tmC, C, cdims, cstr, cbox, cs))
         epi = (mask ? EPI_MASK : 0) | (d.drop_p > 0.f ? EPI_DROP : 0) | (res ? EPI_RES : 0) |
               (d.dtype_c == A3T_BF16 ? EPI_BF16 : 0);
     }
   }
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
 #define A3T_ROW(C2)                                                                                               \
   {gemm_tc_kernel<0, C2>,  gemm_tc_kernel<1, C2>,  gemm_tc_kernel<2, C2>,  gemm_tc_kernel<3, C2>,  gemm_tc_kernel<4, C2>,  \
    gemm_tc_kernel<5, C2>,  gemm_tc_kernel<6, C2>,  gemm_tc_kernel<7, C2>,  gemm_tc_kernel<8, C2>,  gemm_tc_kernel<9, C2>,  \
@@ -1207,7 +1234,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmC, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmC, tmR, p);
     if (e != cudaSuccess) {
       set_error("gemm_tc: launch: %s", cudaGetErrorString(e));
       return A3T_ERR_CUDA;
