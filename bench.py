@@ -205,7 +205,15 @@ def _time_gemms(fn):
         e0.record()
         rc = orig(name, *a)
         e1.record()
-        evs.append((e0, e1, 2.0 * d.M * d.N * d.K * d.batch1 * d.batch2))
+        nb = d.batch1 * d.batch2
+        cs = 2 if d.dtype_c == _lib.A3T_BF16 else 4
+        if d.mode == _lib.GEMM_CONV:      # activations once (taps re-read them from L2), packed weight, output
+            by = 2 * d.M * d.cin + 2 * d.N * d.K + cs * d.M * d.N
+        elif d.mode == _lib.GEMM_WGRAD:   # dy (K x M), x (K x cin), fp32 dW
+            by = 2 * d.K * d.M + 2 * d.K * d.cin + 4 * d.M * d.N
+        else:
+            by = nb * (2 * d.M * d.K + 2 * d.N * d.K + cs * d.M * d.N)
+        evs.append((e0, e1, 2.0 * d.M * d.N * d.K * nb, float(by)))
         return rc
 
     _lib.call = bk.call = timing
@@ -214,8 +222,8 @@ def _time_gemms(fn):
         torch.cuda.synchronize()
     finally:
         _lib.call = bk.call = orig
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
-    return ms, sum(f for _, _, f in evs), len(evs)
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in evs)
+    return ms, sum(f for _, _, f, _ in evs), len(evs), sum(b for _, _, _, b in evs)
 
 
 def run_reference(args):
@@ -396,10 +404,16 @@ def main():
     loss_now = float(stats_host[0] / stats_host[2])
 
     # ---- roofline of the dominant kernel (GEMM) from one instrumented eager step ---------------
-    gemm_ms, gemm_flops, n_gemm = _time_gemms(lambda: trainer.step(static))
+    gemm_ms, gemm_flops, n_gemm, gemm_bytes = _time_gemms(lambda: trainer.step(static))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
@@ -429,7 +443,10 @@ def main():
                        "loss": loss_now, "alg_tflop_per_step_per_gpu": alg_flops_step / 1e12,
                        "step_tensor_frac_of_peak": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / peak},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_unit": "B/launch (DRAM read+write, mean over the step's GEMM launches)",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
+                         "algorithmic_flop_per_launch": gemm_flops / max(n_gemm, 1),
                          "kernel": "a3t_gemm (all dense contractions of the step)", "launches": n_gemm,
                          "how": "CUDA-event pair around every a3t_gemm call of one eager step; FLOPs = 2*M*N*K*batch per call",
                          "peak_source": peak_src},
