@@ -139,15 +139,15 @@ class CudaBackend:
         items = (_lib.PackItem * len(entries))()
         tile, max_taps = 0, 1
         for i, (srcs, pw) in enumerate(entries):
-            if pw.fwd is None or pw.N % len(srcs) or (len(srcs) > 1 and (pw.N // len(srcs)) % 32) or pw.taps > 11:
+            if pw.fwd is None or pw.N % len(srcs) or pw.taps > 11:
                 return None
             it = items[i]
             for j in range(4):
                 it.w[j] = srcs[j].data_ptr() if j < len(srcs) else None
             it.fwd, it.dgrad = pw.fwd.data_ptr(), pw.dgrad.data_ptr()
             it.N, it.C, it.taps, it.seg_rows = pw.N, pw.C, pw.taps, pw.N // len(srcs)
-            it.tile_start, it.tiles_c = tile, (pw.C + 31) // 32
-            tile += ((pw.N + 31) // 32) * it.tiles_c
+            it.tile_start, it.tiles_c = tile, (pw.C + 63) // 64
+            tile += ((pw.N + 63) // 64) * it.tiles_c
             max_taps = max(max_taps, pw.taps)
         table = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.device)
         return dict(table=table, n=len(entries), tiles=tile, max_taps=max_taps, keep=entries)

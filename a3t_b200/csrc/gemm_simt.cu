@@ -194,9 +194,14 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
   }
 }
 
-// batched variant: block -> (item, n tile, c tile) through the items' running tile counts
+// batched variant: block -> (item, n tile, c tile) through the items' running tile counts.
+// 64 x 64 (x taps) tiles staged in shared memory as bf16; both packs are written as 4-byte bf16 pairs so a
+// warp stores 128 contiguous bytes (64 channels of one (n, tap) row for `fwd`, 64 output rows of one
+// (c, tap) row for `dgrad`).  Reads are 16-byte vectors when the rows allow it.
+constexpr int PK_B = 64;
 __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const A3tPackItem* __restrict__ items, int n_items) {
-  extern __shared__ float tile[];
+  extern __shared__ __align__(16) unsigned char pk_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(pk_smem);  // [PK_B][PK_B * taps + 2]
   __shared__ int s_item;
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_items - 1;
@@ -209,38 +214,77 @@ __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const A3tPackIte
   __syncthreads();
   const A3tPackItem it = items[s_item];
   const int local = blockIdx.x - it.tile_start;
-  const int n0 = (local / it.tiles_c) * PK_T, c0 = (local % it.tiles_c) * PK_T;
+  const int n0 = (local / it.tiles_c) * PK_B, c0 = (local % it.tiles_c) * PK_B;
   const int N = it.N, C = it.C, taps = it.taps;
-  const int rowlen = PK_T * taps, ld = rowlen + 1;
-  const int seg = n0 / it.seg_rows;                  // a 32-row tile never straddles two sources
-  const float* __restrict__ w = it.w[seg];
-  const int nb = n0 - seg * it.seg_rows;             // row of the tile inside its source
-  const int seg_n = min(it.seg_rows, N - seg * it.seg_rows);
-  for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
-    int n = idx / rowlen, j = idx - n * rowlen;
-    int c = c0 + j / taps;
-    float v = 0.f;
-    if (nb + n < seg_n && c < C) v = w[((int64_t)(nb + n) * C + c0) * taps + j];
-    tile[n * ld + j] = v;
+  const int rowlen = PK_B * taps, ld = rowlen + 2;   // ld/2 odd: the column walks of the dgrad pass hit distinct banks
+  // output row n0 + n comes from source (n0 + n) / seg_rows (stacked sources; a tile may straddle two of them)
+  const int cw = min(PK_B, C - c0);                  // channels of this tile
+  const int rl = cw * taps;                          // valid floats per row
+  const bool vec = ((C * taps) % 4) == 0 && ((c0 * taps) % 4) == 0 && (rl % 4) == 0 &&
+                   ((((uintptr_t)it.w[0] | (uintptr_t)it.w[1] | (uintptr_t)it.w[2] | (uintptr_t)it.w[3]) & 15) == 0);
+  if (vec) {
+    const int q = rl >> 2;
+    for (int idx = threadIdx.x; idx < PK_B * q; idx += 256) {
+      const int n = idx / q, j = (idx - n * q) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + n < N) {
+        const int sg = (n0 + n) / it.seg_rows, rn = (n0 + n) - sg * it.seg_rows;
+        v = __ldcs(reinterpret_cast<const float4*>(it.w[sg] + ((int64_t)rn * C + c0) * taps + j));
+      }
+      __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(tile + n * ld + j);
+      d[0] = __floats2bfloat162_rn(v.x, v.y);
+      d[1] = __floats2bfloat162_rn(v.z, v.w);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < PK_B * rl; idx += 256) {
+      const int n = idx / rl, j = idx - n * rl;
+      float v = 0.f;
+      if (n0 + n < N) {
+        const int sg = (n0 + n) / it.seg_rows, rn = (n0 + n) - sg * it.seg_rows;
+        v = it.w[sg][((int64_t)rn * C + c0) * taps + j];
+      }
+      tile[n * ld + j] = __float2bfloat16_rn(v);
+    }
   }
   __syncthreads();
   __nv_bfloat16* fwd = (__nv_bfloat16*)it.fwd;
   __nv_bfloat16* dg = (__nv_bfloat16*)it.dgrad;
-  if (fwd) {
-    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
-      int cc = idx % PK_T, r = idx / PK_T;
-      int tap = r % taps, n = r / taps;
-      if (n0 + n < N && nb + n < seg_n && c0 + cc < C)
-        fwd[(int64_t)(n0 + n) * taps * C + (int64_t)tap * C + c0 + cc] = __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = min(PK_B, N - n0);  // valid output rows of this tile
+  if (fwd) {  // fwd[n, tap*C + c]: a warp writes the 64 channels of one (n, tap)
+    const bool pair = (C % 2) == 0;  // 4-byte aligned channel pairs
+    for (int r = warp; r < nrows * taps; r += 8) {
+      const int n = r / taps, tap = r - n * taps;
+      __nv_bfloat16* dst = fwd + (int64_t)(n0 + n) * taps * C + (int64_t)tap * C + c0;
+      const __nv_bfloat16* src = tile + n * ld + tap;
+      const int cc = lane * 2;
+      if (pair && cc + 1 < cw) {
+        __nv_bfloat162 h;
+        h.x = src[cc * taps];
+        h.y = src[(cc + 1) * taps];
+        *reinterpret_cast<__nv_bfloat162*>(dst + cc) = h;
+      } else {
+        if (cc < cw) dst[cc] = src[cc * taps];
+        if (cc + 1 < cw) dst[cc + 1] = src[(cc + 1) * taps];
+      }
     }
   }
-  if (dg) {
-    for (int idx = threadIdx.x; idx < PK_T * rowlen; idx += 256) {
-      int n = idx % PK_T, r = idx / PK_T;
-      int tap = r % taps, cc = r / taps;
-      if (n0 + n < N && nb + n < seg_n && c0 + cc < C)
-        dg[(int64_t)(c0 + cc) * taps * N + (int64_t)(taps - 1 - tap) * N + n0 + n] =
-            __float2bfloat16_rn(tile[n * ld + cc * taps + tap]);
+  if (dg) {   // dgrad[c, (taps-1-tap)*N + n]: a warp writes the 64 rows n of one (c, tap)
+    const bool pair = (N % 2) == 0;
+    for (int r = warp; r < cw * taps; r += 8) {
+      const int cc = r / taps, tap = r - cc * taps;
+      __nv_bfloat16* dst = dg + (int64_t)(c0 + cc) * taps * N + (int64_t)(taps - 1 - tap) * N + n0;
+      const __nv_bfloat16* src = tile + cc * taps + tap;
+      const int n = lane * 2;
+      if (pair && n + 1 < nrows) {
+        __nv_bfloat162 h;
+        h.x = src[n * ld];
+        h.y = src[(n + 1) * ld];
+        *reinterpret_cast<__nv_bfloat162*>(dst + n) = h;
+      } else {
+        if (n < nrows) dst[n] = src[n * ld];
+        if (n + 1 < nrows) dst[n + 1] = src[(n + 1) * ld];
+      }
     }
   }
 }
@@ -274,7 +318,14 @@ extern "C" int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void
 extern "C" int a3t_pack_conv_weights(const A3tPackItem* items, int n_items, int total_tiles, int max_taps, void* stream) {
   A3T_REQUIRE(items && n_items > 0 && total_tiles > 0, "pack_conv_weights: bad args");
   A3T_REQUIRE(max_taps >= 1 && max_taps <= 11, "pack_conv_weights: max_taps=%d out of range (1..11)", max_taps);
-  size_t smem = (size_t)a3t::PK_T * (a3t::PK_T * max_taps + 1) * sizeof(float);
+  size_t smem = (size_t)a3t::PK_B * (a3t::PK_B * max_taps + 2) * sizeof(__nv_bfloat16);
+  if (smem > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(a3t::pack_conv_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+  }
   a3t::pack_conv_weights_kernel<<<total_tiles, 256, smem, (cudaStream_t)stream>>>(items, n_items);
   return a3t::check_launch("pack_conv_weights");
 }

@@ -103,8 +103,8 @@ int a3t_pack_conv_weight(const float* w, int N, int C, int taps, void* fwd_bf16,
 /* Batched form of a3t_pack_conv_weight: ONE launch repacks every GEMM weight of the model after an optimizer
  * step.  `items` is a DEVICE array; an item may stack up to 4 source weights along N (the fused
  * [q+u | q+v | k | v] projection packs [Wq, Wq, Wk, Wv] without materialising the concatenation; seg_rows rows
- * per source, a multiple of 32 when more than one source is used).  tile_start = running count of 32x32 tiles
- * (ceil(N/32) * ceil(C/32) per item); total_tiles = the sum; max_taps = largest taps of any item (<= 11). */
+ * per source).  tile_start = running count of 64x64 tiles
+ * (ceil(N/64) * ceil(C/64) per item); total_tiles = the sum; max_taps = largest taps of any item (<= 11). */
 typedef struct A3tPackItem {
   const float* w[4];
   void* fwd;    /* bf16 (N, taps*C) or NULL */
