@@ -1064,9 +1064,11 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   double best_cost = 1e30;
   const int cands[5] = {256, 192, 128, 64, ((nlim + 15) / 16) * 16};
   for (int cta2 = 0; cta2 <= 1; cta2++) {
-    // measured on B200 (tools/bench_gemm2.py): CTA pairs are not faster than single CTAs for these shapes
-    // (61.9 vs 61.1 us on FFN w_1), so pairs are opt-in until the main loop is no longer delivery-bound
-    if (env_cta ? atoi(env_cta) != cta2 + 1 : cta2 != 0) continue;
+    // measured on B200 (tools/bench_gemm2.py, profiles/r01_gemm_experiments.md): CTA pairs (half the B tile staged per
+    // SM) gain 2-6 % on the K >= 1152 implicit-conv shapes (FFN fwd / dgrad) and lose on the small-K, batched and
+    // weight-gradient shapes, so they are the default for 3-tap convolutions only
+    const bool pair_default = d.mode == A3T_GEMM_CONV && d.taps >= 3 && d.K >= 1024 && p.m_tiles >= 8;
+    if (env_cta ? atoi(env_cta) != cta2 + 1 : (cta2 != 0) != pair_default) continue;
     if (cta2 && p.m_tiles < 2) continue;
     if (cta2 && wg3) continue;
     for (int ci = 0; ci < 5; ci++) {

@@ -515,14 +515,15 @@ __global__ void __launch_bounds__(1024) bn_final_kernel(const double* __restrict
   }
 }
 
+// swish through ex2.approx / rcp.approx: relative error ~1e-6, two orders below the parity gates (1e-4)
 __device__ __forceinline__ float act_fwd(float v, int act) {
-  if (act == A3T_ACT_SWISH) return v / (1.f + expf(-v));
+  if (act == A3T_ACT_SWISH) return __fdividef(v, 1.f + __expf(-v));
   if (act == A3T_ACT_TANH) return tanhf(v);
   return v;
 }
 __device__ __forceinline__ float act_grad(float v, int act) {
   if (act == A3T_ACT_SWISH) {
-    float s = 1.f / (1.f + expf(-v));
+    float s = __fdividef(1.f, 1.f + __expf(-v));
     return s * (1.f + v * (1.f - s));
   }
   if (act == A3T_ACT_TANH) {

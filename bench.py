@@ -157,7 +157,7 @@ class ClockSampler:
 # kernels launched by one C-ABI call (for gpu_launches)
 KERNELS_PER_CALL = {"a3t_layernorm_bwd": 1, "a3t_colsum": 1, "a3t_mask_input_bwd": 2, "a3t_bn_stats": 2,
                     "a3t_bn_act_bwd": 3, "a3t_glu_dwconv_bwd": 2, "a3t_masked_l1_fwd": 2, "a3t_grad_sqnorm": 2,
-                    "a3t_adam_step": 2, "a3t_relpos_softmax_bwd": 2, "a3t_stft_logmel": 2}
+                    "a3t_adam_step": 2, "a3t_stft_logmel": 2}
 
 
 def _count_launches(fn):
@@ -213,7 +213,15 @@ def _time_gemms(fn):
             by = 2 * d.K * d.M + 2 * d.K * d.cin + 4 * d.M * d.N
         else:
             by = nb * (2 * d.M * d.K + 2 * d.N * d.K + cs * d.M * d.N)
-        evs.append((e0, e1, 2.0 * d.M * d.N * d.K * nb, float(by)))
+        if nb > 1:
+            cls = "attention (batched QK^T / PV and their gradients)"
+        elif d.taps == 3:
+            cls = "ffn conv k3 (fwd, dgrad, wgrad)"
+        elif d.taps == 1:
+            cls = "projections / pointwise / head (k1)"
+        else:
+            cls = "postnet conv k5"
+        evs.append((e0, e1, 2.0 * d.M * d.N * d.K * nb, float(by), cls))
         return rc
 
     _lib.call = bk.call = timing
@@ -222,8 +230,12 @@ def _time_gemms(fn):
         torch.cuda.synchronize()
     finally:
         _lib.call = bk.call = orig
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in evs)
-    return ms, sum(f for _, _, f, _ in evs), len(evs), sum(b for _, _, _, b in evs)
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _, _ in evs)
+    by_class = {}
+    for e0, e1, f, _, cls in evs:
+        a = by_class.setdefault(cls, [0, 0.0, 0.0])
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
+    return ms, sum(f for _, _, f, _, _ in evs), len(evs), sum(b for _, _, _, b, _ in evs), by_class
 
 
 def run_reference(args):
@@ -404,7 +416,7 @@ def main():
     loss_now = float(stats_host[0] / stats_host[2])
 
     # ---- roofline of the dominant kernel (GEMM) from one instrumented eager step ---------------
-    gemm_ms, gemm_flops, n_gemm, gemm_bytes = _time_gemms(lambda: trainer.step(static))
+    gemm_ms, gemm_flops, n_gemm, gemm_bytes, gemm_classes = _time_gemms(lambda: trainer.step(static))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -447,6 +459,9 @@ def main():
                          "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
                          "algorithmic_flop_per_launch": gemm_flops / max(n_gemm, 1),
+                         "by_class": {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] / 1e3) / 1e12 if v[1] > 0 else None,
+                                          "frac": (v[2] / (v[1] / 1e3) / 1e12 / peak) if v[1] > 0 and peak else None}
+                                      for k, v in gemm_classes.items()},
                          "kernel": "a3t_gemm (all dense contractions of the step)", "launches": n_gemm,
                          "how": "CUDA-event pair around every a3t_gemm call of one eager step; FLOPs = 2*M*N*K*batch per call",
                          "peak_source": peak_src},
