@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
     const void* __restrict__ ac, const void* __restrict__ bd_raw, int dt_in, const uint8_t* __restrict__ keymask,
     TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* row = sm + (size_t)warp * S;
@@ -64,6 +65,7 @@ template <typename TP, typename TO>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
     const void* __restrict__ dPd, int dt_in, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, float scale,
     float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* row = sm + (size_t)warp * S;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
 template <typename TO>
 __global__ void __launch_bounds__(256) relshift_bwd_kernel(const TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nmat,
                                                            int S) {
+  A3T_PDL_TRIGGER();
   const int64_t per = (int64_t)S * S;
   const int64_t n = nmat * per;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
     const TI* __restrict__ ac, const TI* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
     TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* row = sm + (size_t)warp * S;
@@ -209,6 +213,7 @@ template <typename TP, typename TO, typename TI>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
     const TI* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nrows,
     int S, float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* row = sm + (size_t)warp * S;
@@ -286,6 +291,7 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_
     const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
     __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site, int dbg) {
+  A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Drop dr = make_drop(drop_p, seed, site);
   const int64_t nrows = (int64_t)B * H * S;
@@ -404,6 +410,7 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
     const __nv_bfloat16* __restrict__ dPd, const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dS,
     __nv_bfloat16* __restrict__ dBD, int64_t nrows, int S, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Drop dr = make_drop(drop_p, seed, site);
   for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < nrows; r += (int64_t)gridDim.x * 8) {

@@ -38,6 +38,15 @@ __device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, fl
   else ((float*)p)[i] = v;
 }
 
+// ---- programmatic dependent launch --------------------------------------------------------
+// Every kernel signals at its first instruction that a dependent grid may be scheduled: a kernel launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization (the persistent GEMM) then runs its prologue
+// (barrier init, TMEM allocation, descriptor prefetch) while this grid drains, and blocks in
+// A3T_PDL_WAIT() -- which returns only when this grid has completed and flushed -- before it touches memory.
+// Without the attribute on the dependent's launch both instructions are no-ops.
+#define A3T_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define A3T_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
 // ---- stateless dropout mask (bit-identical twin: oracle/a3t_oracle.py::keep_mask) -----------
 // One 32-bit integer hash of (element-pair index, seed, site) decides TWO consecutive elements: the even
 // element of the pair takes the low 16 bits, the odd one the high 16 bits; keep iff that 16-bit value

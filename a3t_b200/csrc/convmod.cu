@@ -42,6 +42,7 @@ template <typename TU>
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const TU* __restrict__ u, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ z,
                                                              int B, int S, int C, int K) {
+  A3T_PDL_TRIGGER();
   __shared__ float tile[DW_TT + DW_MAXK - 1][DW_TC];
   const int pad = (K - 1) / 2;
   const int ntt = (S + DW_TT - 1) / DW_TT;
@@ -83,6 +84,7 @@ template <typename TU, typename TDU>
 __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __restrict__ dz, const TU* __restrict__ u,
                                                              const float* __restrict__ w, TDU* __restrict__ du,
                                                              float* __restrict__ partial, int B, int S, int C, int K) {
+  A3T_PDL_TRIGGER();
   constexpr int ROWS = DW_TT + DW_MAXK - 1;
   __shared__ float smem_raw[2 * ROWS * DW_TC];
   float (*tdz)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw);                 // dz, rows from t0-(K-1-pad)
@@ -169,6 +171,7 @@ template <typename TU, int KT>
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kt_kernel(const TU* __restrict__ u, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ z,
                                                                 int B, int S, int C) {
+  A3T_PDL_TRIGGER();
   constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2;
   __shared__ __align__(16) float tile[ROWS][DW_TC];
   const int ntt = (S + DW_TT - 1) / DW_TT;
@@ -207,6 +210,7 @@ template <typename TU, typename TDU, int KT>
 __global__ void __launch_bounds__(256) glu_dwconv_bwd_kt_kernel(const float* __restrict__ dz, const TU* __restrict__ u,
                                                                 const float* __restrict__ w, TDU* __restrict__ du,
                                                                 float* __restrict__ partial, int B, int S, int C) {
+  A3T_PDL_TRIGGER();
   constexpr int ROWS = DW_TT + KT - 1, WIN = DW_TPT + KT - 1, pad = (KT - 1) / 2, padr = KT - 1 - pad;
   __shared__ __align__(16) float smem_raw[2 * ROWS * DW_TC > 4 * (KT + 1) * DW_TC ? 2 * ROWS * DW_TC : 4 * (KT + 1) * DW_TC];
   float (*tdz)[DW_TC] = reinterpret_cast<float (*)[DW_TC]>(smem_raw);                 // dz, rows from t0-padr
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kt_kernel(const float* __r
 __global__ void __launch_bounds__(1024) dwconv_bwd_final_kernel(const float* __restrict__ partial,
                                                                 float* __restrict__ dw, float* __restrict__ dbias,
                                                                 int nblk, int C, int K) {
+  A3T_PDL_TRIGGER();
   __shared__ float red[8][128];
   const int col = threadIdx.x & 127, part = threadIdx.x >> 7;
   const int idx = blockIdx.x * 128 + col;

@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(256) mask_input_fwd_kernel(const float* __rest
                                                              const uint8_t* __restrict__ masked,
                                                              const float* __restrict__ mask_feature,
                                                              TY* __restrict__ y, int64_t rows, int C) {
+  A3T_PDL_TRIGGER();
   int64_t n = rows * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) embed_assemble_fwd_kernel(
     const int64_t* __restrict__ tseg, const float* __restrict__ emb, const float* __restrict__ seg,
     float* __restrict__ xs, int B, int Ts, int Tt, int D, float xscale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text) {
+  A3T_PDL_TRIGGER();
   Drop ds = make_drop(drop_p, seed, site_speech);
   Drop dt = make_drop(drop_p, seed, site_text);
   const int S = Ts + Tt;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(
     const int64_t* __restrict__ tseg, float* __restrict__ dspeech_y, float* __restrict__ demb,
     float* __restrict__ dseg, int B, int Ts, int Tt, int D, float xscale, int emb_pad, int seg_pad,
     float drop_p, const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text) {
+  A3T_PDL_TRIGGER();
   Drop ds = make_drop(drop_p, seed, site_speech);
   Drop dt = make_drop(drop_p, seed, site_text);
   const int S = Ts + Tt;

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(FE_THREADS) stft_logmel_kernel(
     const float* __restrict__ wav, const int64_t* __restrict__ ilens, const float* __restrict__ window,
     const float* __restrict__ melmat, const int32_t* __restrict__ mel_range, float* __restrict__ mel,
     int B, int64_t N, int T, int n_fft, int win_length, int hop, int n_mels) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float2 smem[];
   const int NC = n_fft >> 1;
   float2* bufA = smem;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(FE_THREADS) stft_logmel_kernel(
 
 __global__ void olens_kernel(const int64_t* __restrict__ ilens, int64_t* __restrict__ olens, int B, int64_t N,
                              int win_length, int hop) {
+  A3T_PDL_TRIGGER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int64_t il = ilens ? ilens[b] : N;
@@ -140,6 +142,7 @@ __global__ void olens_kernel(const int64_t* __restrict__ ilens, int64_t* __restr
 // ---- collate integer math -----------------------------------------------------------------
 __global__ void align_to_frames_kernel(const float* __restrict__ t_sec, int32_t* __restrict__ frames, int64_t n,
                                        float fs, float hop) {
+  A3T_PDL_TRIGGER();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // torch.floor(fs * t / hop).int(): two correctly-rounded fp32 ops, in this order
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) expand_phone_mask_kernel(
     const uint8_t* __restrict__ phone_mask, const int32_t* __restrict__ align_start,
     const int32_t* __restrict__ align_end, const int64_t* __restrict__ align_len,
     const uint8_t* __restrict__ speech_valid, uint8_t* __restrict__ masked_position, int Ts, int Tt) {
+  A3T_PDL_TRIGGER();
   const int b = blockIdx.x;
   uint8_t* mp = masked_position + (int64_t)b * Ts;
   for (int t = threadIdx.x; t < Ts; t += blockDim.x) mp[t] = 0;
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(256) segment_pos_kernel(const int32_t* __restr
                                                           const int64_t* __restrict__ align_len,
                                                           int64_t* __restrict__ speech_seg,
                                                           int64_t* __restrict__ text_seg, int Ts, int Tt) {
+  A3T_PDL_TRIGGER();
   const int b = blockIdx.x;
   int64_t* sp = speech_seg + (int64_t)b * Ts;
   int64_t* tp = text_seg + (int64_t)b * Tt;

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const A3tGemmDesc d, con
                                                         const float* __restrict__ res0,
                                                         const void* __restrict__ mask0,
                                                         const unsigned long long* __restrict__ seed) {
+  A3T_PDL_TRIGGER();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int bz = blockIdx.z;
@@ -164,6 +165,7 @@ constexpr int PK_T = 32;
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int N, int C, int taps,
                                                                __nv_bfloat16* __restrict__ fwd,
                                                                __nv_bfloat16* __restrict__ dg) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float tile[];  // [PK_T][PK_T * taps + 1]
   const int rowlen = PK_T * taps, ld = rowlen + 1;
   const int n0 = blockIdx.x * PK_T, c0 = blockIdx.y * PK_T;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
 // (c, tap) row for `dgrad`).  Reads are 16-byte vectors when the rows allow it.
 constexpr int PK_B = 64;
 __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const A3tPackItem* __restrict__ items, int n_items) {
+  A3T_PDL_TRIGGER();
   extern __shared__ __align__(16) unsigned char pk_smem[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(pk_smem);  // [PK_B][PK_B * taps + 2]
   __shared__ int s_item;
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const A3tPackIte
 __global__ void qkv4_bias_kernel(const float* __restrict__ bq, const float* __restrict__ bk, const float* __restrict__ bv,
                                  const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ out,
                                  int D) {
+  A3T_PDL_TRIGGER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D) return;
   out[i] = bq[i] + u[i];

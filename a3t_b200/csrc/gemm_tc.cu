@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ Params p) {
+  A3T_PDL_TRIGGER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -417,6 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  A3T_PDL_WAIT();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   const A3tGemmDesc& d = p.d;
 
@@ -1218,20 +1220,28 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
             d.mode, (int)cta2, p.block_n, p.splits, p.stages, p.num_work, epi);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
   if (cta2) {
     int groups = sms / 2;
     int g = p.num_work < groups ? p.num_work : groups;
     cfg.gridDim = dim3(2 * g);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    nattr++;
   } else {
     cfg.gridDim = dim3(p.num_work < sms ? p.num_work : sms);
   }
+  static const bool pdl = !getenv("A3T_NO_PDL");
+  if (pdl && !(p.splits > 1 && !d.c_zeroed)) {  // (the library's own memset node must not be overtaken)
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    nattr++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;

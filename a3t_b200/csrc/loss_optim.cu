@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) masked_l1_partial_kernel(const float* __r
                                                                 const float* __restrict__ y,
                                                                 const uint8_t* __restrict__ mask,
                                                                 double* __restrict__ partial, int64_t rows, int C) {
+  A3T_PDL_TRIGGER();
   __shared__ double sh[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double num = 0.0, den = 0.0;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) masked_l1_partial_kernel(const float* __r
   }
 }
 __global__ void masked_l1_final_kernel(const double* __restrict__ partial, float* __restrict__ out, int nblk) {
+  A3T_PDL_TRIGGER();
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < nblk; i += 32) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
   a = warp_sum_d(a);
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const float* __restr
                                                             const uint8_t* __restrict__ mask,
                                                             const float* __restrict__ den, float* __restrict__ dbefore,
                                                             float* __restrict__ dafter, int64_t rows, int C) {
+  A3T_PDL_TRIGGER();
   const float g = gloss[0] / den[0];
   int64_t n = rows * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const float* __restr
 constexpr int SQ_BLOCKS = 1024;
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g, int64_t n,
                                                              double* __restrict__ partial) {
+  A3T_PDL_TRIGGER();
   __shared__ double sh[8];
   double acc = 0.0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
   }
 }
 __global__ void sqnorm_final_kernel(const double* __restrict__ partial, double* __restrict__ sq, int nblk) {
+  A3T_PDL_TRIGGER();
   double a = 0.0;
   for (int i = threadIdx.x; i < nblk; i += 32) a += partial[i];
   a = warp_sum_d(a);
@@ -110,6 +115,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float base_lr, float model_size, float warmup, float beta1,
                                                    float beta2, float eps, float max_norm, float grad_scale,
                                                    const float* __restrict__ denom) {
+  A3T_PDL_TRIGGER();
   if (denom) grad_scale /= denom[0];
   // total norm of the scaled gradient
   const double norm = sqrt(sq[0]) * (double)grad_scale;
@@ -161,11 +167,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 __global__ void step_advance_kernel(const double* __restrict__ sq, int64_t* __restrict__ step_p, float grad_scale,
                                     const float* __restrict__ denom) {
+  A3T_PDL_TRIGGER();
   if (denom) grad_scale /= denom[0];
   const double norm = sqrt(sq[0]) * (double)grad_scale;
   if (isfinite(norm)) step_p[0] += 1;
 }
 __global__ void seed_advance_kernel(unsigned long long* seed) {
+  A3T_PDL_TRIGGER();
   *seed = *seed * 6364136223846793005ull + 1442695040888963407ull;
 }
 

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(
     TY* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o, int64_t rows, int C,
     float eps, int relu, float out_scale, float drop_p, const unsigned long long* __restrict__ seed,
     uint32_t site) {
+  A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = C >> 2;  // float4 per row
   Drop dr = make_drop(drop_p, seed, site);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_kernel(
     int C, int relu, float out_scale, float drop_p, const unsigned long long* __restrict__ seed,
     uint32_t site, TG* __restrict__ gnext, float gn_scale, float gn_p, uint32_t gn_site,
     float* __restrict__ acc_dgamma, float* __restrict__ acc_dbeta, float* __restrict__ acc_gsum) {
+  A3T_PDL_TRIGGER();
   extern __shared__ float sm[];  // [LN_WARPS][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = C >> 2;
@@ -256,6 +258,7 @@ __device__ __forceinline__ T reduce_rows_128x8(const T* __restrict__ partial, in
 __global__ void __launch_bounds__(1024) reduce_partial_kernel(const float* __restrict__ partial,
                                                               float* __restrict__ out0, float* __restrict__ out1,
                                                               int nblk, int C) {
+  A3T_PDL_TRIGGER();
   __shared__ float red[8][128];
   const int c = blockIdx.x * 128 + (threadIdx.x & 127);
   float t = reduce_rows_128x8<float>(partial, nblk, 2 * C, c, red);
@@ -279,6 +282,7 @@ static int colsum_blocks_host(int64_t rows) {
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ partial,
                                                      int64_t rows, int C, int64_t ldx) {
+  A3T_PDL_TRIGGER();
   int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   int nblk = gridDim.y;
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 }
 __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                             int nblk, int C) {
+  A3T_PDL_TRIGGER();
   __shared__ float red[8][128];
   const int c = blockIdx.x * 128 + (threadIdx.x & 127);
   float t = reduce_rows_128x8<float>(partial, nblk, C, c, red);
@@ -331,6 +336,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ partial,
                                                          int64_t rows, int C, int64_t ldx,
                                                          float* __restrict__ atomic_out = nullptr) {
+  A3T_PDL_TRIGGER();
   constexpr int N = Vec16<T>::N;
   __shared__ float red[8][32 * N + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 __global__ void __launch_bounds__(256) masked_colsum_kernel(const float* __restrict__ x,
                                                             const uint8_t* __restrict__ masked,
                                                             float* __restrict__ partial, int64_t rows, int C) {
+  A3T_PDL_TRIGGER();
   int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   int nblk = gridDim.y;
@@ -420,6 +427,7 @@ __global__ void __launch_bounds__(256) scale_dropout_kernel(const float* __restr
                                                             int64_t n, float scale, float drop_p,
                                                             const unsigned long long* __restrict__ seed,
                                                             uint32_t site) {
+  A3T_PDL_TRIGGER();
   Drop dr = make_drop(drop_p, seed, site);
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -441,6 +449,7 @@ __global__ void __launch_bounds__(256) scale_dropout_kernel(const float* __restr
 // batch statistics independent of the blocking)
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, double* __restrict__ partial,
                                                          int64_t rows, int C) {
+  A3T_PDL_TRIGGER();
   __shared__ double red[8][2][128 + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + tx) * 4;
@@ -486,6 +495,7 @@ __global__ void __launch_bounds__(1024) bn_final_kernel(const double* __restrict
                                                         float* __restrict__ running_var, int64_t* __restrict__ nbt,
                                                         int nblk, int64_t rows, int C, float momentum, float eps,
                                                         int training) {
+  A3T_PDL_TRIGGER();
   __shared__ double red[8][128];
   const int c = blockIdx.x * 128 + (threadIdx.x & 127);
   const bool lead = (threadIdx.x >> 7) == 0;
@@ -541,6 +551,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ res, TY* __restrict__ y,
                                                          int64_t rows, int C, int act, float drop_p,
                                                          const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   Drop dr = make_drop(drop_p, seed, site);
   const int C4 = C >> 2;
   const int64_t n4 = rows * C4;
@@ -573,6 +584,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
                                                              int act, float drop_p,
                                                              const unsigned long long* __restrict__ seed,
                                                              uint32_t site) {
+  A3T_PDL_TRIGGER();
   __shared__ double red[8][2][128 + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + tx) * 4;
@@ -630,6 +642,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
 __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const double* __restrict__ partial,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             float* __restrict__ coef, int nblk, int C) {
+  A3T_PDL_TRIGGER();
   __shared__ double red[8][128];
   const int c = blockIdx.x * 128 + (threadIdx.x & 127);
   double sb = reduce_rows_128x8<double>(partial, nblk, 2 * (int64_t)C, c < C ? c : (int64_t)2 * C, red);
@@ -647,6 +660,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict_
                                                         const float* __restrict__ coef, float* __restrict__ dz,
                                                         int64_t rows, int C, int act, int training, float drop_p,
                                                         const unsigned long long* __restrict__ seed, uint32_t site) {
+  A3T_PDL_TRIGGER();
   Drop dr = make_drop(drop_p, seed, site);
   const int C4 = C >> 2;
   const int64_t n4 = rows * C4;

@@ -8,6 +8,7 @@ namespace a3t {
 // nearest-neighbour stretch x scale, then FIR of length 2*scale+1 (zero pad `scale`)
 __global__ void __launch_bounds__(256) pwg_upsample_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                            float* __restrict__ out, int rows, int64_t T, int scale) {
+  A3T_PDL_TRIGGER();
   const int64_t To = T * scale;
   const int64_t n = (int64_t)rows * To;
   const int taps = 2 * scale + 1;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) pwg_conv1d_kernel(const float* __restrict
                                                          const float* __restrict__ bias, float* __restrict__ out, int B,
                                                          int Cin, int Cout, int64_t T, int K, int dil, int pad_mode,
                                                          int relu_in, float in_scale) {
+  A3T_PDL_TRIGGER();
   const int64_t n = (int64_t)B * Cout * T;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int half = (K - 1) / 2;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(RB_THREADS) pwg_resblock_kernel(
     const float* __restrict__ x, const float* __restrict__ c, const float* __restrict__ w_in_t,
     const float* __restrict__ b_in, const float* __restrict__ w_out_t, const float* __restrict__ b_out,
     float* __restrict__ x_out, float* __restrict__ skip, int64_t T, int dil, int first) {
+  A3T_PDL_TRIGGER();
   constexpr int R = 64, G = 128, A = 80, KIN = 3 * R + A;  // 272
   extern __shared__ float smem[];
   float* sin = smem;               // [KIN][RB_TT]
