@@ -74,8 +74,8 @@ _SIGS = {
     "a3t_mask_input_bwd": [_P, _P, _P, _P, _L, _I, _P],
     "a3t_embed_assemble_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _U, _P],
     "a3t_embed_assemble_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _F, _P, _U, _U, _P],
-    "a3t_relpos_softmax_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
-    "a3t_relpos_softmax_bwd": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_relpos_softmax_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_relpos_softmax_bwd": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_glu_dwconv_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "a3t_dwconv_bwd_blocks": [_I, _I],
     "a3t_glu_dwconv_bwd": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],

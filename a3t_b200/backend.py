@@ -334,67 +334,101 @@ class CudaBackend:
         return dsy, demb, dseg
 
     # ------------------------------------------------------------------ attention
+    def _scores(self, Bn, H, S, device):
+        """(B,H,S,S) score tensor in the activation dtype.  In the tensor-core mode its rows are padded to a
+        multiple of 8 elements (a strided view of a (B,H,S,Sp) buffer): TMA tensor maps need 16-byte aligned
+        rows, and real batches have arbitrary S."""
+        Sp = S if self.act_dtype == torch.float32 else (S + 7) // 8 * 8
+        return torch.empty(Bn, H, S, Sp, dtype=self.act_dtype, device=device)[..., :S]
+
+    @staticmethod
+    def _like(t):
+        """Uninitialised tensor with t's shape AND strides (keeps the row pitch of a score tensor)."""
+        return torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+
+    @classmethod
+    def _as(cls, x, ref):
+        """x laid out with ref's strides (copy only when a caller hands in a differently pitched tensor)."""
+        if x.stride() == ref.stride():
+            return x
+        y = cls._like(ref)
+        y.copy_(x)
+        return y
+
+    @staticmethod
+    def _sstr(t):
+        """(row pitch, batch stride, head stride) of a score tensor."""
+        return t.stride(2), t.stride(0), t.stride(1)
+
     def attn_scores_fwd(self, qkv4, p, H):
-        """qkv4 (B,S,4D) = [q+u | q+v | k | v]; p (S,D).  AC = (q+u)k^T, BDraw = (q+v)p^T, fp32 (B,H,S,S)."""
+        """qkv4 (B,S,4D) = [q+u | q+v | k | v]; p (S,D).  AC = (q+u)k^T, BDraw = (q+v)p^T, (B,H,S,S)."""
         Bn, S, D4 = qkv4.shape
         D = D4 // 4
         dk = D // H
         # score tensors in the activation dtype: fp32 in the parity mode; bf16 in the tensor-core mode, where P
         # itself is stored in bf16 (halves the bytes the memory-bound softmax kernel reads)
-        ac = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
-        bd = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
+        ac, bd = self._scores(Bn, H, S, qkv4.device), self._scores(Bn, H, S, qkv4.device)
+        ld, sb1, sb2 = self._sstr(ac)
         dt = _dt(qkv4)
         common = dict(batch1=Bn, batch2=H, dtype_a=dt, dtype_b=dt, dtype_c=_dt(ac), sa_m=D4, sa_k=1, sa_b1=S * D4,
-                      sa_b2=dk, sc_m=S, sc_n=1, sc_b1=H * S * S, sc_b2=S * S)
+                      sa_b2=dk, sc_m=ld, sc_n=1, sc_b1=sb1, sc_b2=sb2)
         d = self._desc(S, S, dk, sb_n=D4, sb_k=1, sb_b1=S * D4, sb_b2=dk, **common)
         self._gemm(d, qkv4, qkv4, ac, a_off=0, b_off=2 * D)
-        d = self._desc(S, S, dk, sb_n=D, sb_k=1, sb_b1=0, sb_b2=dk, **common)
+        d = self._desc(S, S, dk, sb_n=p.stride(0), sb_k=1, sb_b1=0, sb_b2=dk, **common)
         self._gemm(d, qkv4, p, bd, a_off=D)
         return ac, bd
 
     def relpos_softmax_fwd(self, ac, bd_raw, keymask, scale, *, drop=None):
         Bn, H, S, _ = ac.shape
-        P = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=ac.device)
+        assert ac.stride(3) == 1
+        bd_raw = self._as(bd_raw, ac)
+        P = self._like(ac)
         p, seed, site = self._drop(drop)
-        Pd = torch.empty_like(P) if p > 0 else P
-        call("a3t_relpos_softmax_fwd", _p(ac), _p(bd_raw), _dt(ac), _p(_u8(keymask)), _p(P), _p(Pd), _dt(P), Bn, H, S, scale, p,
-             seed, site, _stream(ac))
+        Pd = self._like(ac) if p > 0 else P
+        ld = ac.stride(2)
+        call("a3t_relpos_softmax_fwd", _p(ac), _p(bd_raw), _dt(ac), _p(_u8(keymask)), _p(P), _p(Pd), _dt(P), Bn, H, S, ld,
+             scale, p, seed, site, _stream(ac))
         return P, Pd
 
     def attn_pv_fwd(self, pd, qkv4, H):
         Bn, S, D4 = qkv4.shape
         D = D4 // 4
         dk = D // H
+        ld, sb1, sb2 = self._sstr(pd)
         ctx = torch.empty(Bn, S, D, dtype=self.act_dtype, device=qkv4.device)
-        d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=_dt(pd), dtype_b=_dt(qkv4), dtype_c=_dt(ctx), sa_m=S,
-                       sa_k=1, sa_b1=H * S * S, sa_b2=S * S, sb_n=1, sb_k=D4, sb_b1=S * D4, sb_b2=dk, sc_m=D, sc_n=1,
+        d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=_dt(pd), dtype_b=_dt(qkv4), dtype_c=_dt(ctx), sa_m=ld,
+                       sa_k=1, sa_b1=sb1, sa_b2=sb2, sb_n=1, sb_k=D4, sb_b1=S * D4, sb_b2=dk, sc_m=D, sc_n=1,
                        sc_b1=S * D, sc_b2=dk)
         self._gemm(d, pd, qkv4, ctx, b_off=3 * D)
         return ctx
 
     def attn_pv_bwd(self, dctx, pd, qkv4, H, dqkv4):
-        """dPd = dctx v^T (fp32);  dV = Pd^T dctx -> dqkv4[..., 3D:]."""
+        """dPd = dctx v^T;  dV = Pd^T dctx -> dqkv4[..., 3D:]."""
         Bn, S, D4 = qkv4.shape
         D = D4 // 4
         dk = D // H
-        dPd = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=qkv4.device)
+        dPd = self._scores(Bn, H, S, qkv4.device)
+        ld, sb1, sb2 = self._sstr(dPd)
         d = self._desc(S, S, dk, batch1=Bn, batch2=H, dtype_a=_dt(dctx), dtype_b=_dt(qkv4), dtype_c=_dt(dPd), sa_m=D,
-                       sa_k=1, sa_b1=S * D, sa_b2=dk, sb_n=D4, sb_k=1, sb_b1=S * D4, sb_b2=dk, sc_m=S, sc_n=1,
-                       sc_b1=H * S * S, sc_b2=S * S)
+                       sa_k=1, sa_b1=S * D, sa_b2=dk, sb_n=D4, sb_k=1, sb_b1=S * D4, sb_b2=dk, sc_m=ld, sc_n=1,
+                       sc_b1=sb1, sc_b2=sb2)
         self._gemm(d, dctx, qkv4, dPd, b_off=3 * D)
+        ld, sb1, sb2 = self._sstr(pd)
         d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=_dt(pd), dtype_b=_dt(dctx), dtype_c=_dt(dqkv4), sa_m=1,
-                       sa_k=S, sa_b1=H * S * S, sa_b2=S * S, sb_n=1, sb_k=D, sb_b1=S * D, sb_b2=dk, sc_m=D4, sc_n=1,
+                       sa_k=ld, sa_b1=sb1, sa_b2=sb2, sb_n=1, sb_k=D, sb_b1=S * D, sb_b2=dk, sc_m=D4, sc_n=1,
                        sc_b1=S * D4, sc_b2=dk)
         self._gemm(d, pd, dctx, dqkv4, c_off=3 * D)
         return dPd
 
     def relpos_softmax_bwd(self, dPd, P, scale, *, drop=None):
         Bn, H, S, _ = P.shape
-        dS = torch.empty(Bn, H, S, S, dtype=self.act_dtype, device=P.device)
-        dBD = torch.empty_like(dS)
+        assert P.stride(3) == 1
+        dPd = self._as(dPd, P)
+        dS, dBD = self._like(P), self._like(P)
         p, seed, site = self._drop(drop)
-        call("a3t_relpos_softmax_bwd", _p(dPd), _dt(dPd), _p(P), _dt(P), _p(dS), _p(dBD), _dt(dS), Bn, H, S, scale, p, seed, site,
-             _stream(P))
+        ld = P.stride(2)
+        call("a3t_relpos_softmax_bwd", _p(dPd), _dt(dPd), _p(P), _dt(P), _p(dS), _p(dBD), _dt(dS), Bn, H, S, ld, scale, p,
+             seed, site, _stream(P))
         return dS, dBD
 
     def attn_scores_bwd(self, dS, dBD, qkv4, p, H, dqkv4):
@@ -403,15 +437,17 @@ class CudaBackend:
         D = D4 // 4
         dk = D // H
         dts, dtq = _dt(dS), _dt(qkv4)
-        a_row = dict(sa_m=S, sa_k=1, sa_b1=H * S * S, sa_b2=S * S)   # A[i, j]
-        a_col = dict(sa_m=1, sa_k=S, sa_b1=H * S * S, sa_b2=S * S)   # A^T
+        dBD = self._as(dBD, dS)
+        ld, sb1, sb2 = self._sstr(dS)
+        a_row = dict(sa_m=ld, sa_k=1, sa_b1=sb1, sa_b2=sb2)   # A[i, j]
+        a_col = dict(sa_m=1, sa_k=ld, sa_b1=sb1, sa_b2=sb2)   # A^T
         c_qkv = dict(sc_m=D4, sc_n=1, sc_b1=S * D4, sc_b2=dk)
         b_qkv = dict(sb_n=1, sb_k=D4, sb_b1=S * D4, sb_b2=dk)
         base = dict(batch1=Bn, batch2=H, dtype_a=dts, dtype_b=dtq, dtype_c=_dt(dqkv4))
         self._gemm(self._desc(S, dk, S, **base, **a_row, **b_qkv, **c_qkv), dS, qkv4, dqkv4, b_off=2 * D, c_off=0)
         self._gemm(self._desc(S, dk, S, **base, **a_col, **b_qkv, **c_qkv), dS, qkv4, dqkv4, b_off=0, c_off=2 * D)
         d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=dts, dtype_b=_dt(p), dtype_c=_dt(dqkv4), **a_row,
-                       sb_n=1, sb_k=D, sb_b1=0, sb_b2=dk, **c_qkv)
+                       sb_n=1, sb_k=p.stride(0), sb_b1=0, sb_b2=dk, **c_qkv)
         self._gemm(d, dBD, p, dqkv4, c_off=D)
         tmp = torch.empty(Bn, S, D, dtype=torch.float32, device=qkv4.device)
         d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=dts, dtype_b=dtq, dtype_c=A3T_F32, **a_col, **b_qkv,

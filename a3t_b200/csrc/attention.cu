@@ -11,17 +11,19 @@ constexpr int SM_WARPS = 4;
 
 // rel_shift gather: padded view (S, S+1) with a zero first column, reinterpreted as (S+1, S),
 // first row dropped.  shifted[i,j] = padded_flat[(i+1)*S + j].
-__device__ __forceinline__ float bd_shifted(const void* __restrict__ bd, int dt, int64_t mat, int S, int i, int j) {
+// `ld` = row pitch of the (S, S) score matrices in elements (>= S; a multiple of 8 keeps every row 16-byte
+// aligned for the TMA tensor maps of the contractions when S itself is not)
+__device__ __forceinline__ float bd_shifted(const void* __restrict__ bd, int dt, int64_t mat, int S, int64_t ld, int i, int j) {
   int64_t f = (int64_t)(i + 1) * S + j;
   int r = (int)(f / (S + 1));
   int c = (int)(f - (int64_t)r * (S + 1));
-  return c == 0 ? 0.f : load_as_f32(bd, dt, mat + (int64_t)r * S + (c - 1));
+  return c == 0 ? 0.f : load_as_f32(bd, dt, mat + (int64_t)r * ld + (c - 1));
 }
 
 template <typename TP>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
     const void* __restrict__ ac, const void* __restrict__ bd_raw, int dt_in, const uint8_t* __restrict__ keymask,
-    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, int64_t ld, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
     const uint8_t* km = keymask + (int64_t)b * S;
     float mx = -FLT_MAX;
     for (int j = lane; j < S; j += 32) {
-      float s = (load_as_f32(ac, dt_in, r * S + j) + bd_shifted(bd_raw, dt_in, bh * (int64_t)S * S, S, i, j)) * scale;
+      float s = (load_as_f32(ac, dt_in, r * ld + j) + bd_shifted(bd_raw, dt_in, bh * (int64_t)S * ld, S, ld, i, j)) * scale;
       if (!km[j]) s = -FLT_MAX;  // finfo(float32).min
       row[j] = s;
       mx = fmaxf(mx, s);
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
     const float inv = 1.f / sum;
     for (int j = lane; j < S; j += 32) {
       float p = km[j] ? row[j] * inv : 0.f;
-      P[r * S + j] = from_f32<TP>(p);
-      if (dr.on) Pd[r * S + j] = from_f32<TP>(drop_apply(dr, (unsigned long long)(r * S + j), p));
-      else if (Pd != P) Pd[r * S + j] = from_f32<TP>(p);
+      P[r * ld + j] = from_f32<TP>(p);
+      if (dr.on) Pd[r * ld + j] = from_f32<TP>(drop_apply(dr, (unsigned long long)(r * S + j), p));
+      else if (Pd != P) Pd[r * ld + j] = from_f32<TP>(p);
     }
     __syncwarp();
   }
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_kernel(
 // dS[i,j] = P * (dPu - sum_j dPu*P) * scale ; dPu = dPd*keep/(1-p)
 template <typename TP, typename TO>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
-    const void* __restrict__ dPd, int dt_in, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, float scale,
-    float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+    const void* __restrict__ dPd, int dt_in, const TP* __restrict__ P, TO* __restrict__ dS, int64_t nrows, int S, int64_t ld,
+    float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -73,15 +75,15 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
   for (int64_t r = (int64_t)blockIdx.x * SM_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * SM_WARPS) {
     float dot = 0.f;
     for (int j = lane; j < S; j += 32) {
-      float g = load_as_f32(dPd, dt_in, r * S + j);
+      float g = load_as_f32(dPd, dt_in, r * ld + j);
       if (dr.on) g = drop_keep(dr, (unsigned long long)(r * S + j)) ? g * dr.inv_keep : 0.f;
       row[j] = g;
-      dot += g * to_f32<TP>(P[r * S + j]);
+      dot += g * to_f32<TP>(P[r * ld + j]);
     }
     dot = warp_sum(dot);
     for (int j = lane; j < S; j += 32) {
-      float p = to_f32<TP>(P[r * S + j]);
-      dS[r * S + j] = from_f32<TO>(p * (row[j] - dot) * scale);
+      float p = to_f32<TP>(P[r * ld + j]);
+      dS[r * ld + j] = from_f32<TO>(p * (row[j] - dot) * scale);
     }
     __syncwarp();
   }
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_kernel(
 // dBD_raw[r, cc] = dS at the inverse rel_shift position (0 where BD_raw is never read)
 template <typename TO>
 __global__ void __launch_bounds__(256) relshift_bwd_kernel(const TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nmat,
-                                                           int S) {
+                                                           int S, int64_t ld) {
   A3T_PDL_TRIGGER();
   const int64_t per = (int64_t)S * S;
   const int64_t n = nmat * per;
@@ -99,8 +101,9 @@ __global__ void __launch_bounds__(256) relshift_bwd_kernel(const TO* __restrict_
     int64_t m = idx / per;
     int64_t e = idx - m * per;
     int r = (int)(e / S), cc = (int)(e - (int64_t)r * S);
-    int64_t f = (int64_t)r * (S + 1) + cc + 1 - S;  // flat index into the (S,S) shifted matrix
-    dBD[idx] = f >= 0 ? dS[m * per + f] : from_f32<TO>(0.f);
+    int64_t f = (int64_t)r * (S + 1) + cc + 1 - S;  // flat index into the dense (S,S) shifted matrix
+    const int64_t fr = f / S, fc = f - fr * S;
+    dBD[m * S * ld + (int64_t)r * ld + cc] = f >= 0 ? dS[m * S * ld + fr * ld + fc] : from_f32<TO>(0.f);
   }
 }
 
@@ -140,7 +143,7 @@ __device__ __forceinline__ void load_p4<__nv_bfloat16>(const __nv_bfloat16* p, f
 template <typename TP, typename TI>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
     const TI* __restrict__ ac, const TI* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
-    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    TP* __restrict__ P, TP* __restrict__ Pd, int B, int H, int S, int64_t ld, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
@@ -152,9 +155,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
     const int i = (int)(r % S);
     const int64_t bh = r / S;
     const int b = (int)(bh / H);
-    const TI* acr = ac + r * S;
-    const TI* bd0 = bd_raw + (bh * S + i) * (int64_t)S + (S - 1 - i);   // + j       for j <= i
-    const TI* bd1 = bd_raw + (bh * S + i + 1) * (int64_t)S - (i + 2);   // + j       for j >= i+2
+    const TI* acr = ac + r * ld;
+    const TI* bd0 = bd_raw + (bh * S + i) * ld + (S - 1 - i);   // + j       for j <= i
+    const TI* bd1 = bd_raw + (bh * S + i + 1) * ld - (i + 2);   // + j       for j >= i+2
     const uint8_t* km = keymask + (int64_t)b * S;
     float mx = -FLT_MAX;
     for (int j = lane * 4; j < S; j += 128) {
@@ -190,16 +193,16 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
       const float4 t = *reinterpret_cast<float4*>(row + j);
       const uchar4 k4 = *reinterpret_cast<const uchar4*>(km + j);
       float pv[4] = {k4.x ? t.x * inv : 0.f, k4.y ? t.y * inv : 0.f, k4.z ? t.z * inv : 0.f, k4.w ? t.w * inv : 0.f};
-      store_p4<TP>(P + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+      store_p4<TP>(P + r * ld + j, pv[0], pv[1], pv[2], pv[3]);
       if (dr.on) {
         const unsigned long long idx0 = (unsigned long long)(r * S + j);
         bool kp[4];
         drop_keep4(dr, drop_fold(idx0), kp);
 #pragma unroll
         for (int e = 0; e < 4; e++) pv[e] = kp[e] ? pv[e] * dr.inv_keep : 0.f;
-        store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+        store_p4<TP>(Pd + r * ld + j, pv[0], pv[1], pv[2], pv[3]);
       } else if (Pd != P) {
-        store_p4<TP>(Pd + r * S + j, pv[0], pv[1], pv[2], pv[3]);
+        store_p4<TP>(Pd + r * ld + j, pv[0], pv[1], pv[2], pv[3]);
       }
     }
     __syncwarp();
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_fwd_v4_kernel(
 template <typename TP, typename TO, typename TI>
 __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
     const TI* __restrict__ dPd, const TP* __restrict__ P, TO* __restrict__ dS, TO* __restrict__ dBD, int64_t nrows,
-    int S, float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
+    int S, int64_t ld, float scale, float drop_p, const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
     float dot = 0.f;
     for (int j = lane * 4; j < S; j += 128) {
       float g[4];
-      load_p4<TI>(dPd + r * S + j, g);
+      load_p4<TI>(dPd + r * ld + j, g);
       float pv[4];
-      load_p4<TP>(P + r * S + j, pv);
+      load_p4<TP>(P + r * ld + j, pv);
       if (dr.on) {
         const unsigned long long idx0 = (unsigned long long)(r * S + j);
         bool kp[4];
@@ -237,15 +240,15 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
       *reinterpret_cast<float4*>(row + j) = make_float4(g[0], g[1], g[2], g[3]);
     }
     dot = warp_sum(dot);
-    TO* d0 = dBD + r * S + (S - 1 - i);          // + j   for j <= i
-    TO* d1 = dBD + (r + 1) * S - (i + 2);        // + j   for j >= i+2 (row i+1 of the same matrix)
+    TO* d0 = dBD + r * ld + (S - 1 - i);         // + j   for j <= i
+    TO* d1 = dBD + (r + 1) * ld - (i + 2);       // + j   for j >= i+2 (row i+1 of the same matrix)
     for (int j = lane * 4; j < S; j += 128) {
       float pv[4];
-      load_p4<TP>(P + r * S + j, pv);
+      load_p4<TP>(P + r * ld + j, pv);
       const float4 g4 = *reinterpret_cast<float4*>(row + j);
       const float o[4] = {pv[0] * (g4.x - dot) * scale, pv[1] * (g4.y - dot) * scale, pv[2] * (g4.z - dot) * scale,
                           pv[3] * (g4.w - dot) * scale};
-      store_p4<TO>(dS + r * S + j, o[0], o[1], o[2], o[3]);
+      store_p4<TO>(dS + r * ld + j, o[0], o[1], o[2], o[3]);
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const int jj = j + e;
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) relpos_softmax_bwd_v4_kernel(
       }
     }
     if (i == 0) {  // BD_raw[0, 0..S-2] is never read by the forward
-      for (int j = lane; j < S - 1; j += 32) dBD[r * S + j] = from_f32<TO>(0.f);
+      for (int j = lane; j < S - 1; j += 32) dBD[r * ld + j] = from_f32<TO>(0.f);
     }
     __syncwarp();
   }
@@ -289,28 +292,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int NIT, bool FULL>  // FULL: S == 128 * NIT, no tail guards
 __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_kernel(
     const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
-    __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, float scale, float drop_p,
+    __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, int ld, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site, int dbg) {
   A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Drop dr = make_drop(drop_p, seed, site);
   const int64_t nrows = (int64_t)B * H * S;
-  const int SS = S * S;  // S <= 2048
+  const int SS = S * ld;  // elements per score matrix (S <= 2048, ld = row pitch, ld % 4 == 0)
   const float c2 = scale * 1.4426950408889634f;  // softmax in base 2: exp(s - m) = 2^((s - m) log2 e)
   for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < nrows; r += (int64_t)gridDim.x * 8) {
     const int i = (int)(r % S);
     const int64_t bh = r / S;
     const int b = (int)(bh / H);
-    const __nv_bfloat16* acr = ac + r * S;
-    __nv_bfloat16* const Pr = P + r * S;
-    __nv_bfloat16* const Pdr = Pd + r * S;
+    const __nv_bfloat16* acr = ac + r * ld;
+    __nv_bfloat16* const Pr = P + r * ld;
+    __nv_bfloat16* const Pdr = Pd + r * ld;
     const unsigned long long ebase = (unsigned long long)(r * S);
     const __nv_bfloat16* G = bd_raw + bh * SS;
     const uint8_t* km = keymask + (int64_t)b * S;
-    // windows: groups left of the gap start at G[o + j], all others at G[o + j - 1]; 8-byte aligned bases
-    const int o = (i + 1) * (S - 1);
-    const int basel = o & ~3, baser = (o - 1) & ~3;
-    const int dl = o & 3, dg = (o - 1) & 3;
+    // windows: key j left of the gap reads G[ol + j] (row i of BD_raw), right of it G[og + j] (row i+1);
+    // with a dense matrix (ld == S) og == ol - 1: one contiguous slice with the zero of key i+1 squeezed out
+    const int ol = i * ld + (S - 1 - i), og = (i + 1) * ld - (i + 2);
+    const int basel = ol & ~3, baser = og & ~3;
+    const int dl = ol & 3, dg = og & 3;
     uint2 a[NIT], w01[NIT], w23[NIT];
     uint32_t kw[NIT];
 #pragma unroll
@@ -346,12 +350,11 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_
           const bool hi = (d & 2) != 0;
           const uint32_t q0 = hi ? w01[it].y : w01[it].x, q1 = hi ? w23[it].x : w01[it].y, q2 = hi ? w23[it].y : w23[it].x;
           bf16x4_to_f32(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), bv);
-        } else {                   // the one group per row that holds the zero at key i+1
-          const uint32_t w[4] = {w01[it].x, w01[it].y, w23[it].x, w23[it].y};
+        } else {                   // the one group per row that holds the zero at key i+1: element loads
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const int jj = j + e;
-            bv[e] = jj == i + 1 ? 0.f : bf16_at(w, d + (jj <= i ? e + 1 : e));
+            bv[e] = jj == i + 1 ? 0.f : __bfloat162float(G[(jj <= i ? ol : og) + jj]);
           }
         }
 #pragma unroll
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_
 template <int NIT, bool FULL>
 __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_kernel(
     const __nv_bfloat16* __restrict__ dPd, const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dS,
-    __nv_bfloat16* __restrict__ dBD, int64_t nrows, int S, float scale, float drop_p,
+    __nv_bfloat16* __restrict__ dBD, int64_t nrows, int S, int ld, float scale, float drop_p,
     const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -420,8 +423,8 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
     for (int it = 0; it < NIT; it++) {
       // groups past the end of the row re-load the last group (no branch in the load phase); they are zeroed below
       const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
-      gw[it] = __ldcs(reinterpret_cast<const uint2*>(dPd + r * S + j));
-      pw[it] = __ldcs(reinterpret_cast<const uint2*>(P + r * S + j));
+      gw[it] = __ldcs(reinterpret_cast<const uint2*>(dPd + r * ld + j));
+      pw[it] = __ldcs(reinterpret_cast<const uint2*>(P + r * ld + j));
       if (!FULL && lane * 4 + it * 128 >= S) pw[it] = make_uint2(0u, 0u);
     }
     float g[NIT][4];
@@ -443,8 +446,10 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
       }
     }
     dot = warp_sum(dot);
-    // inverse rel_shift: row i of dS is the contiguous run dBD_flat[o .. o+S-2] (matrix-local) with key i+1 dropped
-    __nv_bfloat16* const run = dBD + (r - i) * S + (int64_t)(i + 1) * (S - 1);
+    // inverse rel_shift: keys j <= i go to row i of dBD_raw at column S-1-i+j, keys j >= i+2 to row i+1 at
+    // column j-i-2 (key i+1 is dropped); contiguous when the matrix is dense
+    __nv_bfloat16* const runl = dBD + r * ld + (S - 1 - i);      // + j
+    __nv_bfloat16* const rung = dBD + (r + 1) * ld - (i + 2);    // + j
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
       const int j = lane * 4 + it * 128;
@@ -453,28 +458,28 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
         bf16x4_to_f32(pw[it].x, pw[it].y, pv);
         __nv_bfloat162 h[2] = {__floats2bfloat162_rn(pv[0] * (g[it][0] - dot) * scale, pv[1] * (g[it][1] - dot) * scale),
                                __floats2bfloat162_rn(pv[2] * (g[it][2] - dot) * scale, pv[3] * (g[it][3] - dot) * scale)};
-        *reinterpret_cast<uint2*>(dS + r * S + j) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(dS + r * ld + j) = *reinterpret_cast<const uint2*>(h);
         const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(h);
         if (j + 3 <= i) {
 #pragma unroll
-          for (int e = 0; e < 4; e++) run[j + e] = hv[e];
+          for (int e = 0; e < 4; e++) runl[j + e] = hv[e];
         } else if (j >= i + 2) {
           if (i + 1 < S) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) run[j + e - 1] = hv[e];
+            for (int e = 0; e < 4; e++) rung[j + e] = hv[e];
           }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const int jj = j + e;
-            if (jj <= i) run[jj] = hv[e];
-            else if (jj >= i + 2 && i + 1 < S) run[jj - 1] = hv[e];
+            if (jj <= i) runl[jj] = hv[e];
+            else if (jj >= i + 2 && i + 1 < S) rung[jj] = hv[e];
           }
         }
       }
     }
     if (i == 0) {  // BD_raw[0, 0..S-2] is never read by the forward
-      for (int j = lane; j < S - 1; j += 32) dBD[r * S + j] = __float2bfloat16_rn(0.f);
+      for (int j = lane; j < S - 1; j += 32) dBD[r * ld + j] = __float2bfloat16_rn(0.f);
     }
   }
 }
@@ -484,9 +489,11 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_bwd_reg_
 using namespace a3t;
 
 extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dtype_in, const uint8_t* keymask, void* P,
-                                      void* Pd, int dtype_p, int B, int H, int S, float scale, float drop_p,
+                                      void* Pd, int dtype_p, int B, int H, int S, int ld, float scale, float drop_p,
                                       const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(ac && bd_raw && keymask && P && Pd, "relpos_softmax_fwd: null pointer");
+  if (ld == 0) ld = S;
+  A3T_REQUIRE(ld >= S, "relpos_softmax_fwd: row pitch %d < S=%d", ld, S);
   A3T_REQUIRE(drop_p == 0.f || (seed && Pd != P), "relpos_softmax_fwd: dropout needs a seed and a separate Pd");
   A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_fwd: S=%d out of range", S);
   A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_fwd: bad input dtype");
@@ -495,25 +502,27 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
-  const bool v4 = (S % 4) == 0 && ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
+  const bool v4 = (S % 4) == 0 && (ld % 4) == 0 &&
+                  ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
   if (v4 && dtype_p == A3T_BF16 && dtype_in == A3T_BF16 && S <= 2048 && (((uintptr_t)bd_raw & 15) == 0) &&
       !getenv("A3T_SOFTMAX_SMEM")) {
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
 #define A3T_SM_FWD_REG(NIT, FULL)                                                                               \
   relpos_softmax_fwd_reg_kernel<NIT, FULL><<<rb, 256, 0, st>>>((const __nv_bfloat16*)ac, (const __nv_bfloat16*)bd_raw, keymask, \
-                                                         (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p,  \
+                                                         (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, ld, scale, drop_p,  \
                                                          seed, site, getenv("A3T_SM_DBG") ? atoi(getenv("A3T_SM_DBG")) : 0)
     if (S == 128 * 9) A3T_SM_FWD_REG(9, true);
     else if (S <= 128 * 5) A3T_SM_FWD_REG(5, false);
     else if (S <= 128 * 9) A3T_SM_FWD_REG(9, false);
+    else if (S <= 128 * 14) A3T_SM_FWD_REG(14, false);
     else A3T_SM_FWD_REG(16, false);
     return check_launch("relpos_softmax_fwd");
   }
   if (v4 && smem <= 48 * 1024) {
 #define A3T_SM_FWD(TPT, TIT)                                                                              \
   relpos_softmax_fwd_v4_kernel<TPT, TIT><<<blocks, SM_WARPS * 32, smem, st>>>(                            \
-      (const TIT*)ac, (const TIT*)bd_raw, keymask, (TPT*)P, (TPT*)Pd, B, H, S, scale, drop_p, seed, site)
+      (const TIT*)ac, (const TIT*)bd_raw, keymask, (TPT*)P, (TPT*)Pd, B, H, S, ld, scale, drop_p, seed, site)
     if (dtype_p == A3T_BF16 && dtype_in == A3T_BF16) A3T_SM_FWD(__nv_bfloat16, __nv_bfloat16);
     else if (dtype_p == A3T_BF16) A3T_SM_FWD(__nv_bfloat16, float);
     else if (dtype_in == A3T_BF16) A3T_SM_FWD(float, __nv_bfloat16);
@@ -524,74 +533,77 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(relpos_softmax_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     relpos_softmax_fwd_kernel<__nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
-        ac, bd_raw, dtype_in, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, scale, drop_p, seed, site);
+        ac, bd_raw, dtype_in, keymask, (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, ld, scale, drop_p, seed, site);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(relpos_softmax_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     relpos_softmax_fwd_kernel<float><<<blocks, SM_WARPS * 32, smem, st>>>(ac, bd_raw, dtype_in, keymask, (float*)P,
-                                                                         (float*)Pd, B, H, S, scale, drop_p, seed, site);
+                                                                         (float*)Pd, B, H, S, ld, scale, drop_p, seed, site);
   }
   return check_launch("relpos_softmax_fwd");
 }
 
 template <typename TP, typename TO>
-static int softmax_bwd_launch(const void* dPd, int dtype_in, const void* P, void* dS, void* dBD, int B, int H, int S,
+static int softmax_bwd_launch(const void* dPd, int dtype_in, const void* P, void* dS, void* dBD, int B, int H, int S, int ld,
                               float scale, float drop_p, const unsigned long long* seed, uint32_t site, cudaStream_t st) {
   int64_t nrows = (int64_t)B * H * S;
   int blocks = (int)((nrows + SM_WARPS - 1) / SM_WARPS);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)SM_WARPS * S * sizeof(float);
-  if ((S % 4) == 0 && smem <= 48 * 1024 && ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0)) {
+  if ((S % 4) == 0 && (ld % 4) == 0 && smem <= 48 * 1024 && ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0)) {
     if (dtype_in == A3T_BF16)
       relpos_softmax_bwd_v4_kernel<TP, TO, __nv_bfloat16><<<blocks, SM_WARPS * 32, smem, st>>>(
-          (const __nv_bfloat16*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, scale, drop_p, seed, site);
+          (const __nv_bfloat16*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, ld, scale, drop_p, seed, site);
     else
       relpos_softmax_bwd_v4_kernel<TP, TO, float><<<blocks, SM_WARPS * 32, smem, st>>>(
-          (const float*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, scale, drop_p, seed, site);
+          (const float*)dPd, (const TP*)P, (TO*)dS, (TO*)dBD, nrows, S, ld, scale, drop_p, seed, site);
     return check_launch("relpos_softmax_bwd");
   }
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(relpos_softmax_bwd_kernel<TP, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, dtype_in, (const TP*)P, (TO*)dS, nrows, S,
+  relpos_softmax_bwd_kernel<TP, TO><<<blocks, SM_WARPS * 32, smem, st>>>(dPd, dtype_in, (const TP*)P, (TO*)dS, nrows, S, ld,
                                                                         scale, drop_p, seed, site);
   int rc = check_launch("relpos_softmax_bwd");
   if (rc) return rc;
   int64_t n = nrows * S;
   int64_t b2 = (n + 255) / 256;
   if (b2 > 148 * 16) b2 = 148 * 16;
-  relshift_bwd_kernel<TO><<<(int)b2, 256, 0, st>>>((const TO*)dS, (TO*)dBD, (int64_t)B * H, S);
+  relshift_bwd_kernel<TO><<<(int)b2, 256, 0, st>>>((const TO*)dS, (TO*)dBD, (int64_t)B * H, S, ld);
   return check_launch("relshift_bwd");
 }
 
 extern "C" int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void* P, int dtype_p, void* dS, void* dBD,
-                                      int dtype_o, int B, int H, int S, float scale, float drop_p,
+                                      int dtype_o, int B, int H, int S, int ld, float scale, float drop_p,
                                       const unsigned long long* seed, uint32_t site, void* stream) {
   A3T_REQUIRE(dPd && P && dS && dBD, "relpos_softmax_bwd: null pointer");
+  if (ld == 0) ld = S;
+  A3T_REQUIRE(ld >= S, "relpos_softmax_bwd: row pitch %d < S=%d", ld, S);
   A3T_REQUIRE(drop_p == 0.f || seed, "relpos_softmax_bwd: dropout needs a seed");
   A3T_REQUIRE(S > 0 && S <= 12000, "relpos_softmax_bwd: S=%d out of range", S);
   A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_bwd: bad input dtype");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype_in == A3T_BF16 && dtype_p == A3T_BF16 && dtype_o == A3T_BF16 && (S % 4) == 0 && S <= 2048 &&
+  if (dtype_in == A3T_BF16 && dtype_p == A3T_BF16 && dtype_o == A3T_BF16 && (S % 4) == 0 && (ld % 4) == 0 && S <= 2048 &&
       ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0) && !getenv("A3T_SOFTMAX_SMEM")) {
     const int64_t nrows = (int64_t)B * H * S;
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
 #define A3T_SM_BWD_REG(NIT, FULL)                                                                                      \
   relpos_softmax_bwd_reg_kernel<NIT, FULL><<<rb, 256, 0, st>>>((const __nv_bfloat16*)dPd, (const __nv_bfloat16*)P,        \
-                                                         (__nv_bfloat16*)dS, (__nv_bfloat16*)dBD, nrows, S, scale, \
+                                                         (__nv_bfloat16*)dS, (__nv_bfloat16*)dBD, nrows, S, ld, scale, \
                                                          drop_p, seed, site)
     if (S == 128 * 9) A3T_SM_BWD_REG(9, true);
     else if (S <= 128 * 5) A3T_SM_BWD_REG(5, false);
     else if (S <= 128 * 9) A3T_SM_BWD_REG(9, false);
+    else if (S <= 128 * 14) A3T_SM_BWD_REG(14, false);
     else A3T_SM_BWD_REG(16, false);
     return check_launch("relpos_softmax_bwd");
   }
   if (dtype_p == A3T_BF16 && dtype_o == A3T_BF16)
-    return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dPd, dtype_in, P, dS, dBD, B, H, S, ld, scale, drop_p, seed, site, st);
   if (dtype_p == A3T_F32 && dtype_o == A3T_F32)
-    return softmax_bwd_launch<float, float>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<float, float>(dPd, dtype_in, P, dS, dBD, B, H, S, ld, scale, drop_p, seed, site, st);
   if (dtype_p == A3T_BF16 && dtype_o == A3T_F32)
-    return softmax_bwd_launch<__nv_bfloat16, float>(dPd, dtype_in, P, dS, dBD, B, H, S, scale, drop_p, seed, site, st);
+    return softmax_bwd_launch<__nv_bfloat16, float>(dPd, dtype_in, P, dS, dBD, B, H, S, ld, scale, drop_p, seed, site, st);
   set_error("relpos_softmax_bwd: unsupported dtype combination");
   return A3T_ERR_UNSUPPORTED;
 }

@@ -183,14 +183,16 @@ int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, const int64_t*
  *   s[i,j] = (AC[i,j] + BDraw_shifted[i,j]) * scale ; key j invalid -> finfo(f32).min
  *   P = softmax_j(s), zeroed at invalid keys;  Pd = dropout(P)   (Pd may alias P when p == 0)
  * AC/BD (B,H,S,S) of dtype_in (fp32 in the parity mode, bf16 in the tensor-core mode: same rounding as P);
- * keymask (B,S) uint8, 1 = valid; P, Pd dtype_p. */
+ * keymask (B,S) uint8, 1 = valid; P, Pd dtype_p.  ld = row pitch in elements of all four (B,H,S,ld) tensors
+ * (0 = dense, ld == S); the host side pads it to a multiple of 8 so that every score row is 16-byte aligned for
+ * the TMA tensor maps of the attention contractions whatever S is. */
 int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dtype_in, const uint8_t* keymask, void* P,
-                           void* Pd, int dtype_p, int B, int H, int S, float scale, float drop_p,
+                           void* Pd, int dtype_p, int B, int H, int S, int ld, float scale, float drop_p,
                            const unsigned long long* seed, uint32_t site, void* stream);
 /* dS = P * (dPu - sum_j dPu*P) * scale with dPu = dPd*keep/(1-p);  dBD_raw = inverse rel_shift of
- * dS.  dPd dtype_in; dS, dBD dtype_o (B,H,S,S). */
+ * dS.  dPd dtype_in; dS, dBD dtype_o (B,H,S,ld); ld as in the forward. */
 int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void* P, int dtype_p, void* dS, void* dBD,
-                           int dtype_o, int B, int H, int S, float scale, float drop_p,
+                           int dtype_o, int B, int H, int S, int ld, float scale, float drop_p,
                            const unsigned long long* seed, uint32_t site, void* stream);
 
 /* Conformer conv module core (conformer/convolution.py:70-75): GLU over channel halves of

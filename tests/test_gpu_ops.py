@@ -194,10 +194,15 @@ def test_relpos_softmax_bf16_register_kernels(cuda_lib, ob, B, H, S):
     keymask = torch.ones(B, S, dtype=torch.bool)
     keymask[0, S - 5:] = False
     sc = 0.125
+    # the backend's own score tensors: rows padded to a multiple of 8 elements (strided views) when S % 8 != 0
+    acc, bdc = bb._scores(B, H, S, "cuda"), bb._scores(B, H, S, "cuda")
+    acc.copy_(ac)
+    bdc.copy_(bd)
+    assert acc.stride(2) % 8 == 0
     for dr in (None, (0.2, 6)):
         Po, Pdo = obb.relpos_softmax_fwd(ac.float(), bd.float(), keymask, sc, drop=dr)
-        Pc, Pdc = bb.relpos_softmax_fwd(ac.cuda(), bd.cuda(), keymask.cuda(), sc, drop=dr)
-        assert Pc.dtype == torch.bfloat16
+        Pc, Pdc = bb.relpos_softmax_fwd(acc, bdc, keymask.cuda(), sc, drop=dr)
+        assert Pc.dtype == torch.bfloat16 and Pc.stride() == acc.stride()
         close(Pc, Po, atol=1e-6, rtol=1e-2)
         close(Pdc, Pdo, atol=1e-6, rtol=1e-2)
         if dr is not None:
@@ -205,7 +210,7 @@ def test_relpos_softmax_bf16_register_kernels(cuda_lib, ob, B, H, S):
         assert float(Pc[0, :, :, S - 5:].abs().max()) == 0.0
         dP = g(B, H, S, S, seed=3).to(torch.bfloat16)
         dSo, _ = obb.relpos_softmax_bwd(dP.float(), Pc.float().cpu(), sc, drop=dr)
-        dSc, dBc = bb.relpos_softmax_bwd(dP.cuda(), Pc, sc, drop=dr)
+        dSc, dBc = bb.relpos_softmax_bwd(dP.cuda(), Pc, sc, drop=dr)   # dense dP is re-laid out to P's pitch
         close(dSc, dSo, atol=2e-3 * float(dSo.abs().max()), rtol=2e-2)
         # inverse rel_shift of the kernel's own dS: the vjp of the oracle's rel_shift is a pure scatter
         x = torch.zeros(B, H, S, S, requires_grad=True)
