@@ -98,35 +98,88 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_kernel(
     an[i] = make_float4(0, 0, 0, 0);
   }
   const float scale_keep = out_scale * dr.inv_keep;
-  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LN_WARPS) {
-    const float mean = mean_i[row], rstd = rstd_i[row];
+  // Row prefetch: while a warp works on row r, the x / dy / dres pieces of ITS next row are already in flight
+  // (cp.async into a per-thread staging slot; every lane later reads back only what it copied itself, so
+  // cp.async.wait_group is the only synchronisation).  Layout [slot][array][i][thread] x 16 bytes: conflict-free.
+  // The staging area is reused as the reduction scratch after the row loop.
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(sm);
+  constexpr uint32_t ARR_BYTES = MAXV * LN_WARPS * 32 * 16;   // one array of one slot
+  constexpr uint32_t SLOT_BYTES = 3 * ARR_BYTES;              // x, dres, dy
+  const uint32_t my = stage0 + threadIdx.x * 16;
+  const int64_t rstride = (int64_t)gridDim.x * LN_WARPS;
+  auto issue = [&](int64_t row, int slot) {
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        const uint32_t d0 = my + slot * SLOT_BYTES + i * (LN_WARPS * 32 * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(x + row * C + c4 * 4) : "memory");
+        if (dres)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + ARR_BYTES), "l"(dres + row * C + c4 * 4) : "memory");
+        if constexpr (sizeof(TDY) == 2)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 2 * ARR_BYTES), "l"(dy + row * C + c4 * 4) : "memory");
+        else
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 2 * ARR_BYTES), "l"(dy + row * C + c4 * 4) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp;
+  int slot = 0;
+  float mean_n = 0.f, rstd_n = 0.f;
+  if (row < rows) {
+    issue(row, 0);
+    mean_n = mean_i[row];
+    rstd_n = rstd_i[row];
+  }
+  for (; row < rows; row += rstride, slot ^= 1) {
+    const float mean = mean_n, rstd = rstd_n;
+    if (row + rstride < rows) {
+      issue(row + rstride, slot ^ 1);
+      mean_n = mean_i[row + rstride];
+      rstd_n = rstd_i[row + rstride];
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     float xh[MAXV][4], dh[MAXV][4];
     float4 rres[MAXV];
     float s1 = 0.f, s2 = 0.f;
-    if (dres) {  // issued up front: the loads overlap the statistics instead of following the warp reductions
+    const uint32_t sb = my + slot * SLOT_BYTES;
+    if (dres) {
 #pragma unroll
       for (int i = 0; i < MAXV; i++) {
         int c4 = lane + i * 32;
-        if (c4 < nv) rres[i] = __ldcs(reinterpret_cast<const float4*>(dres + row * C) + c4);
+        if (c4 < nv)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(rres[i].x), "=f"(rres[i].y), "=f"(rres[i].z), "=f"(rres[i].w)
+                       : "r"(sb + ARR_BYTES + i * (LN_WARPS * 32 * 16)));
       }
     }
 #pragma unroll
     for (int i = 0; i < MAXV; i++) {
       int c4 = lane + i * 32;
       if (c4 < nv) {
-        const float4 xv = reinterpret_cast<const float4*>(x + row * C)[c4];
+        float4 xv;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(xv.x), "=f"(xv.y), "=f"(xv.z), "=f"(xv.w)
+                     : "r"(sb + i * (LN_WARPS * 32 * 16)));
         const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident: not kept in registers
         const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
         const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
         float g[4];
         const int64_t idx0 = row * C + c4 * 4;
         if constexpr (sizeof(TDY) == 2) {
-          const uint2 t = *reinterpret_cast<const uint2*>(dy + idx0);
+          uint2 t;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(sb + 2 * ARR_BYTES + i * (LN_WARPS * 32 * 16)));
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
           float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
           g[0] = f0.x; g[1] = f0.y; g[2] = f1.x; g[3] = f1.y;
         } else {
-          const float4 t = *reinterpret_cast<const float4*>(dy + idx0);
+          float4 t;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                       : "r"(sb + 2 * ARR_BYTES + i * (LN_WARPS * 32 * 16)));
           g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
         }
         if (dr.on) {
@@ -201,7 +254,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_kernel(
       }
     }
   }
-  // block reduce the parameter gradients (and the column sums of gnext)
+  // block reduce the parameter gradients (and the column sums of gnext); the staging slots are dead
+  __syncthreads();
   const int nacc = gnext ? 3 : 2;
   float* sg = sm + (size_t)warp * 3 * C;
 #pragma unroll
@@ -739,15 +793,22 @@ extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, c
   A3T_REQUIRE(!gsum || gnext, "layernorm_bwd: gsum without gnext");
   cudaStream_t st = (cudaStream_t)stream;
   int nblk = a3t_layernorm_bwd_blocks(rows);
-  size_t smem = (size_t)LN_WARPS * 3 * C * sizeof(float);
+  // two prefetch slots of 3 arrays x MAXV x 256 threads x 16 B, reused as [LN_WARPS][3][C] reduction scratch
+  const int mv = C <= 384 ? 3 : 4;
+  size_t smem = (size_t)2 * 3 * mv * LN_WARPS * 32 * 16;
+  if (smem < (size_t)LN_WARPS * 3 * C * sizeof(float)) smem = (size_t)LN_WARPS * 3 * C * sizeof(float);
 #define A3T_LN_BWD2(T, MV, TG)                                                                                       \
-  ln_bwd_kernel<T, MV, TG><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx, partial, \
-                                                              rows, C, relu, out_scale, drop_p, seed, site, (TG*)gnext,  \
-                                                              gnext_scale, gnext_drop_p, gnext_site, dgamma, dbeta, gsum)
+  {                                                                                                                  \
+    cudaFuncSetAttribute(ln_bwd_kernel<T, MV, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    ln_bwd_kernel<T, MV, TG><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx,   \
+                                                                partial, rows, C, relu, out_scale, drop_p, seed, site, \
+                                                                (TG*)gnext, gnext_scale, gnext_drop_p, gnext_site,   \
+                                                                dgamma, dbeta, gsum);                                 \
+  }
 #define A3T_LN_BWD(T, MV)                                        \
   do {                                                           \
-    if (gnext && dtype_gnext == A3T_BF16) A3T_LN_BWD2(T, MV, __nv_bfloat16); \
-    else A3T_LN_BWD2(T, MV, float);                              \
+    if (gnext && dtype_gnext == A3T_BF16) A3T_LN_BWD2(T, MV, __nv_bfloat16) \
+    else A3T_LN_BWD2(T, MV, float)                               \
   } while (0)
   if (dtype_dy == A3T_BF16) {
     if (C <= 384) A3T_LN_BWD(__nv_bfloat16, 3);
