@@ -90,6 +90,31 @@ def test_attention_contractions_tc(bes, B, H, S, dk):
     close(dq_t, dq_s, tol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,S,dk", [(2, 2, 100, 64), (1, 2, 1692, 192)])
+def test_attention_contractions_tc_any_length(bes, B, H, S, dk):
+    """S % 8 != 0: the backend's score tensors carry a row pitch padded to 8 elements, so every attention
+    contraction still qualifies for the tcgen05 kernel (IMPL_TC raises instead of falling back)."""
+    tc, simt = bes
+    D = H * dk
+    qkv4, p = g(B, S, 4 * D, seed=1, scale=0.5), g(S, D, seed=2, scale=0.5)
+    ac_t, bd_t = tc.attn_scores_fwd(qkv4, p, H)
+    ac_s, bd_s = simt.attn_scores_fwd(qkv4, p, H)
+    assert ac_t.stride(2) % 8 == 0 and ac_t.shape == (B, H, S, S)
+    close(ac_t, ac_s, tol=1e-2)
+    close(bd_t, bd_s, tol=1e-2)
+    Pd = tc._scores(B, H, S, "cuda")
+    Pd.copy_(torch.softmax(g(B, H, S, S, seed=3, dtype=torch.float32), -1))
+    close(tc.attn_pv_fwd(Pd, qkv4, H), simt.attn_pv_fwd(Pd, qkv4, H), tol=1e-2)
+    dctx = g(B, S, D, seed=4)
+    dq_t, dq_s = torch.zeros_like(qkv4), torch.zeros_like(qkv4)
+    close(tc.attn_pv_bwd(dctx, Pd, qkv4, H, dq_t), simt.attn_pv_bwd(dctx, Pd, qkv4, H, dq_s), tol=1e-2)
+    dS, dBD = tc._scores(B, H, S, "cuda"), tc._scores(B, H, S, "cuda")
+    dS.copy_(g(B, H, S, S, seed=5, scale=0.1))
+    dBD.copy_(g(B, H, S, S, seed=6, scale=0.1))
+    close(tc.attn_scores_bwd(dS, dBD, qkv4, p, H, dq_t), simt.attn_scores_bwd(dS, dBD, qkv4, p, H, dq_s))
+    close(dq_t, dq_s, tol=1e-2)
+
+
 def test_tc_is_what_auto_picks(cuda_lib):
     """AUTO dispatch must select the tensor-core kernel for the FFN shapes of the paper config."""
     from a3t_b200.backend import CudaBackend

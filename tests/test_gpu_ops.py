@@ -218,6 +218,40 @@ def test_relpos_softmax_bf16_register_kernels(cuda_lib, ob, B, H, S):
         assert torch.equal(dBc.float().cpu(), x.grad)
 
 
+@pytest.mark.parametrize("B,H,S", [(2, 2, 19), (1, 2, 131), (1, 1, 70)])
+def test_relpos_softmax_bf16_odd_lengths_and_padded_rows(cuda_lib, ob, B, H, S):
+    """Sequence lengths that are not multiples of 4 / 8 take the scalar kernels on PITCHED score tensors
+    (rows padded to 8 elements, ld != S), including the separate inverse-rel_shift kernel; one utterance has
+    every key padded (the reference then returns an all-zero attention row, attention.py:79-86)."""
+    from a3t_b200.backend import CudaBackend
+
+    bb = CudaBackend("cuda:0", torch.bfloat16, seed=42)
+    obb = OracleBackend(seed=42)
+    ac = g(B, H, S, S, seed=1, scale=2.0).to(torch.bfloat16)
+    bd = g(B, H, S, S, seed=2, scale=2.0).to(torch.bfloat16)
+    keymask = torch.ones(B, S, dtype=torch.bool)
+    keymask[0, S - 2:] = False
+    keymask[B - 1, :] = False          # fully padded utterance
+    acc, bdc = bb._scores(B, H, S, "cuda"), bb._scores(B, H, S, "cuda")
+    acc.copy_(ac)
+    bdc.copy_(bd)
+    if S % 8:
+        assert acc.stride(2) != S
+    for dr in (None, (0.3, 9)):
+        Po, Pdo = obb.relpos_softmax_fwd(ac.float(), bd.float(), keymask, 0.2, drop=dr)
+        Pc, Pdc = bb.relpos_softmax_fwd(acc, bdc, keymask.cuda(), 0.2, drop=dr)
+        close(Pc, Po, atol=1e-6, rtol=1e-2)
+        close(Pdc, Pdo, atol=1e-6, rtol=1e-2)
+        assert float(Pc[B - 1].abs().max()) == 0.0
+        dP = g(B, H, S, S, seed=3).to(torch.bfloat16)
+        dSo, _ = obb.relpos_softmax_bwd(dP.float(), Pc.float().cpu(), 0.2, drop=dr)
+        dSc, dBc = bb.relpos_softmax_bwd(dP.cuda(), Pc, 0.2, drop=dr)
+        close(dSc, dSo, atol=2e-3 * max(float(dSo.abs().max()), 1e-6), rtol=2e-2)
+        x = torch.zeros(B, H, S, S, requires_grad=True)
+        O.rel_shift(x).backward(dSc.float().cpu())
+        assert torch.equal(dBc.float().cpu(), x.grad)
+
+
 def test_rel_shift_index_map_is_exact(be):
     """BD' = rel_shift(BD) must be an exact gather (no arithmetic): feed integers, AC = 0, and
     compare the pre-softmax ordering through a one-hot trick."""
