@@ -37,6 +37,7 @@ def timing(name, *a):
     evs.append((key, e0, e1, 2.0 * d.M * d.N * d.K * d.batch1 * d.batch2))
     return rc
 _lib.call = bk.call = timing
+torch.cuda._sleep(int(1.9e9 * 0.06))  # GPU stays behind the host: event pairs hold kernel time only
 tr.step(batch)
 torch.cuda.synchronize()
 _lib.call = bk.call = orig
