@@ -277,12 +277,6 @@ __device__ __forceinline__ void bf16x4_to_f32(uint32_t w0, uint32_t w1, float (&
   v[0] = __uint_as_float(w0 << 16); v[1] = __uint_as_float(w0 & 0xFFFF0000u);
   v[2] = __uint_as_float(w1 << 16); v[3] = __uint_as_float(w1 & 0xFFFF0000u);
 }
-// element `idx` (0..7) of the 8 bf16 held in words w[0..3]
-__device__ __forceinline__ float bf16_at(const uint32_t (&w)[4], int idx) {
-  const uint32_t word = idx < 4 ? (idx < 2 ? w[0] : w[1]) : (idx < 6 ? w[2] : w[3]);
-  return __uint_as_float((idx & 1) ? (word & 0xFFFF0000u) : (word << 16));
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -293,7 +287,7 @@ template <int NIT, bool FULL>  // FULL: S == 128 * NIT, no tail guards
 __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_kernel(
     const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ bd_raw, const uint8_t* __restrict__ keymask,
     __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int B, int H, int S, int ld, float scale, float drop_p,
-    const unsigned long long* __restrict__ seed, uint32_t site, int dbg) {
+    const unsigned long long* __restrict__ seed, uint32_t site) {
   A3T_PDL_TRIGGER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Drop dr = make_drop(drop_p, seed, site);
@@ -323,10 +317,10 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_
       // their scores are forced to -inf below and their stores are skipped
       const int j = FULL ? lane * 4 + it * 128 : min(lane * 4 + it * 128, S - 4);
       {
-        a[it] = (dbg & 4) ? make_uint2(0u, 0u) : __ldcs(reinterpret_cast<const uint2*>(acr + j));
+        a[it] = __ldcs(reinterpret_cast<const uint2*>(acr + j));
         const int x4 = ((j + 3 <= i) ? basel : baser) + j;
-        w01[it] = (dbg & 1) ? make_uint2(0u, 0u) : __ldg(reinterpret_cast<const uint2*>(G + x4));
-        w23[it] = (x4 + 8 <= SS && !(dbg & 1)) ? __ldg(reinterpret_cast<const uint2*>(G + x4 + 4)) : make_uint2(0u, 0u);
+        w01[it] = __ldg(reinterpret_cast<const uint2*>(G + x4));
+        w23[it] = (x4 + 8 <= SS) ? __ldg(reinterpret_cast<const uint2*>(G + x4 + 4)) : make_uint2(0u, 0u);
         kw[it] = *reinterpret_cast<const uint32_t*>(km + j);  // consumed only after every load is in flight
       }
     }
@@ -376,7 +370,7 @@ __global__ void __launch_bounds__(256, NIT <= 9 ? 2 : 1) relpos_softmax_fwd_reg_
     for (int it = 0; it < NIT; it++) {
       {
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[it][e] = (dbg & 2) ? v[it][e] - mx : ex2_approx(v[it][e] - mx);
+        for (int e = 0; e < 4; e++) v[it][e] = ex2_approx(v[it][e] - mx);
         sum += (v[it][0] + v[it][1]) + (v[it][2] + v[it][3]);
       }
     }
@@ -511,7 +505,7 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
 #define A3T_SM_FWD_REG(NIT, FULL)                                                                               \
   relpos_softmax_fwd_reg_kernel<NIT, FULL><<<rb, 256, 0, st>>>((const __nv_bfloat16*)ac, (const __nv_bfloat16*)bd_raw, keymask, \
                                                          (__nv_bfloat16*)P, (__nv_bfloat16*)Pd, B, H, S, ld, scale, drop_p,  \
-                                                         seed, site, getenv("A3T_SM_DBG") ? atoi(getenv("A3T_SM_DBG")) : 0)
+                                                         seed, site)
     if (S == 128 * 9) A3T_SM_FWD_REG(9, true);
     else if (S <= 128 * 5) A3T_SM_FWD_REG(5, false);
     else if (S <= 128 * 9) A3T_SM_FWD_REG(9, false);
