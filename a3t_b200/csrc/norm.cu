@@ -799,7 +799,11 @@ extern "C" int a3t_layernorm_bwd(const void* dy, int dtype_dy, const float* x, c
   if (smem < (size_t)LN_WARPS * 3 * C * sizeof(float)) smem = (size_t)LN_WARPS * 3 * C * sizeof(float);
 #define A3T_LN_BWD2(T, MV, TG)                                                                                       \
   {                                                                                                                  \
-    cudaFuncSetAttribute(ln_bwd_kernel<T, MV, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    static int smem_set = 0; /* per instantiation: raise the dynamic shared-memory limit once */                     \
+    if (smem_set < (int)smem) {                                                                                      \
+      cudaFuncSetAttribute(ln_bwd_kernel<T, MV, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+      smem_set = (int)smem;                                                                                          \
+    }                                                                                                                \
     ln_bwd_kernel<T, MV, TG><<<nblk, LN_WARPS * 32, smem, st>>>((const T*)dy, x, mean, rstd, gamma, beta, dres, dx,   \
                                                                 partial, rows, C, relu, out_scale, drop_p, seed, site, \
                                                                 (TG*)gnext, gnext_scale, gnext_drop_p, gnext_site,   \

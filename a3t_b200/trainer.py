@@ -60,6 +60,7 @@ class DataParallelTrainer:
         self._update_fn = update_fn
         self.stats = self.flat_g[self.n:]
         self._plan, self._plan_tried, self._qkv4 = None, False, []
+        self._rest = None
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """One optimizer step on this rank's shard of the global batch.  Returns the device tensor
@@ -74,7 +75,9 @@ class DataParallelTrainer:
         # into its views; only the small vectors (biases, norms, embeddings) are copied in afterwards
         self.flat_g.zero_()
         G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews)
-        rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
+        if self._rest is None:  # which gradients were not written in place is a property of the graph, not of the step
+            self._rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
+        rest = self._rest
         torch._foreach_copy_([self.gviews[n] for n in rest], [G[n].view(self.gviews[n].shape) for n in rest])
         self.stats[0:1].copy_(loss).mul_(float(B))
         self.stats[1:2].copy_(loss).mul_(float(B))
