@@ -120,3 +120,25 @@ def test_clip_adam_matches_torch():
     pp = p.clone()
     O.clip_adam_step(pp, g.clone(), m, v, 1, sched_lr)
     assert torch.allclose(pp, ref_p.detach(), atol=1e-7)
+
+
+def test_dropout_hash_statistics():
+    """The stateless dropout mask (one 32-bit hash per element PAIR, 16 bits each; device twin in
+    csrc/common.cuh) keeps with probability 1-p, the two elements of a pair are uncorrelated, and different
+    sites / seeds give unrelated masks."""
+    n = 1 << 20
+    for p in (0.1, 0.2, 0.5):
+        m = O.keep_mask(n, p, seed=1234567, site=3).numpy().astype(np.float64)
+        q = 1.0 - np.floor(p * 65536.0) / 65536.0           # 16-bit threshold
+        assert abs(m.mean() - q) < 4.0 * np.sqrt(q * (1 - q) / n)
+        a, b = m[0::2] - q, m[1::2] - q                      # the two halves of one hash
+        assert abs((a * b).mean()) < 4.0 * q * (1 - q) / np.sqrt(n / 2)
+        c = m[1::2][:-1] - q                                 # neighbours from different hashes
+        d = m[2::2] - q
+        assert abs((c * d[: c.size]).mean()) < 4.0 * q * (1 - q) / np.sqrt(n / 2)
+        m2 = O.keep_mask(n, p, seed=1234567, site=4).numpy().astype(np.float64)
+        m3 = O.keep_mask(n, p, seed=1234568, site=3).numpy().astype(np.float64)
+        for other in (m2, m3):
+            assert abs(((m - q) * (other - q)).mean()) < 4.0 * q * (1 - q) / np.sqrt(n)
+    assert bool(O.keep_mask(17, 0.0, 1, 1).all())
+
