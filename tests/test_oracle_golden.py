@@ -122,7 +122,7 @@ def test_clip_adam_matches_torch():
     assert torch.allclose(pp, ref_p.detach(), atol=1e-7)
 
 
-def test_dropout_hash_statistics():
+def test_dropout_pair_hash_independence():
     """The stateless dropout mask (one 32-bit hash per element PAIR, 16 bits each; device twin in
     csrc/common.cuh) keeps with probability 1-p, the two elements of a pair are uncorrelated, and different
     sites / seeds give unrelated masks."""
