@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 A3T_F32, A3T_BF16 = 0, 1
 ACT_NONE, ACT_SWISH, ACT_TANH = 0, 1, 2
 GEMM_PLAIN, GEMM_CONV, GEMM_WGRAD = 0, 1, 2
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_PAIR = 0, 1, 2, 3
 
 
 class A3TError(RuntimeError):
@@ -61,6 +61,7 @@ _SIGS = {
     "a3t_version": [],
     "a3t_gemm": [C.POINTER(GemmDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "a3t_gemm_tc_supported": [C.POINTER(GemmDesc), _P, _P, _P],
+    "a3t_gemm_fallback_count": [_I],
     "a3t_pack_conv_weight": [_P, _I, _I, _I, _P, _P, _P],
     "a3t_pack_conv_weights": [_P, _I, _I, _I, _P],
     "a3t_qkv4_bias": [_P, _P, _P, _P, _P, _P, _I, _P],
@@ -72,8 +73,8 @@ _SIGS = {
     "a3t_scale_dropout": [_P, _P, _I, _L, _F, _F, _P, _U, _P],
     "a3t_mask_input_fwd": [_P, _P, _P, _P, _I, _L, _I, _P],
     "a3t_mask_input_bwd": [_P, _P, _P, _P, _L, _I, _P],
-    "a3t_embed_assemble_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _U, _P],
-    "a3t_embed_assemble_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _F, _P, _U, _U, _P],
+    "a3t_embed_assemble_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _U, _I, _I, _P, _P],
+    "a3t_embed_assemble_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _F, _P, _U, _U, _I, _I, _P],
     "a3t_relpos_softmax_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_relpos_softmax_bwd": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_glu_dwconv_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -97,7 +98,7 @@ _SIGS = {
 }
 # entry points that return a count / flag rather than a status code
 _PLAIN_INT = {"a3t_version", "a3t_layernorm_bwd_blocks", "a3t_colsum_blocks", "a3t_dwconv_bwd_blocks",
-              "a3t_gemm_tc_supported"}
+              "a3t_gemm_tc_supported", "a3t_gemm_fallback_count"}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["a3t_last_error"])
 

@@ -11,6 +11,7 @@ checker used by the tests) so the two can be compared call by call.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional, Tuple
 
@@ -39,9 +40,13 @@ def _stream(t: torch.Tensor):
 
 
 def _u8(t: torch.Tensor) -> torch.Tensor:
-    """bool/uint8 -> contiguous uint8 view (no copy for bool)."""
-    t = t.contiguous()
-    return t.view(torch.uint8) if t.dtype == torch.bool else t
+    """Mask tensor -> contiguous uint8 (no copy for bool / uint8).  Any other dtype (int64 / float masks built by
+    hand) is converted with `!= 0`, which is what the reference's `masked_fill` / `eq(0)` see."""
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    if t.dtype == torch.uint8:
+        return t.contiguous()
+    return (t != 0).to(torch.uint8).contiguous()
 
 
 class PackedWeight:
@@ -71,6 +76,9 @@ class CudaBackend:
         # Slices are valid until the next `begin_backward()`.
         self._arena = torch.zeros(1 << 20, dtype=torch.float32, device=self.device)
         self._arena_off = 0
+        # bit 0: token id outside the embedding table, bit 1: segment id outside it (set by the embedding kernel,
+        # read by `check_ids()`; torch raises IndexError at the same place)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------ helpers
     def begin_backward(self):
@@ -96,6 +104,31 @@ class CudaBackend:
 
     def advance_seed(self):
         call("a3t_seed_advance", _p(self.seed), _stream(self.seed))
+
+    def seed_snapshot(self) -> torch.Tensor:
+        """Device copy of the current dropout seed.  Dropout masks are never stored: every kernel re-derives them
+        from the seed it is handed, so a backward pass that may run after the master seed has advanced
+        (`model(**batch)` ... `loss.backward()`) must be given the seed its forward used."""
+        return self.seed.clone()
+
+    @contextlib.contextmanager
+    def using_seed(self, seed: torch.Tensor):
+        """Run the enclosed kernels with `seed` (a device int64[1]) instead of the master seed."""
+        prev, self.seed = self.seed, seed
+        try:
+            yield
+        finally:
+            self.seed = prev
+
+    def check_ids(self):
+        """Raise IndexError if an embedding kernel saw a token / segment id outside its table since the last
+        check (synchronises; call it where the host synchronises anyway, e.g. inference)."""
+        f = int(self.err_flag.item())
+        if f:
+            self.err_flag.zero_()
+            what = [w for b, w in ((1, "token id outside the text embedding table"),
+                                   (2, "segment id outside the segment embedding table (more than 499 phones?)")) if f & b]
+            raise IndexError("a3t_b200: " + "; ".join(what))
 
     def _drop(self, drop):
         if drop is None or drop[0] <= 0.0:
@@ -316,7 +349,8 @@ class CudaBackend:
         p, seed, s1 = self._drop(drop_speech)
         _, _, s2 = self._drop(drop_text)
         call("a3t_embed_assemble_fwd", _p(speech_y), _p(text), _p(sseg), _p(tseg), _p(emb), _p(seg), _p(xs), Bn, Ts,
-             Tt, D, xscale, p, seed, s1, s2, _stream(xs))
+             Tt, D, xscale, p, seed, s1, s2, emb.shape[0], seg.shape[0] if seg is not None else 0, _p(self.err_flag),
+             _stream(xs))
         return xs
 
     def embed_assemble_bwd(self, dxs, text, sseg, tseg, V, nseg, xscale, emb_pad, seg_pad, *, drop_speech=None,
@@ -330,7 +364,7 @@ class CudaBackend:
         p, seed, s1 = self._drop(drop_speech)
         _, _, s2 = self._drop(drop_text)
         call("a3t_embed_assemble_bwd", _p(dxs), _p(text), _p(sseg), _p(tseg), _p(dsy), _p(demb), _p(dseg), Bn, Ts, Tt,
-             D, xscale, emb_pad, seg_pad, p, seed, s1, s2, _stream(dxs))
+             D, xscale, emb_pad, seg_pad, p, seed, s1, s2, V, nseg, _stream(dxs))
         return dsy, demb, dseg
 
     # ------------------------------------------------------------------ attention

@@ -74,11 +74,19 @@ def phones_masking(xs_pad, src_mask, align_start, align_end, align_start_lengths
     lens = align_start_lengths.to(device=dev, dtype=torch.int64).contiguous()
     a_s = align_start.to(device=dev, dtype=torch.int32).contiguous()
     a_e = align_end.to(device=dev, dtype=torch.int32).contiguous()
+    # branch order of the reference (collate_fn.py:353-376): mlm_prob == 1 -> mean_phn_span == 0 -> per-utterance
+    # (span_boundary if given, else the sampler)
     if mlm_prob == 1.0:
         return valid.bool(), None
+    if mean_phn_span == 0:
+        # speech-only batches (collate_fn.py:357-361): one frame-level draw shared by the batch; a given
+        # span_boundary is ignored on this branch, as in the reference
+        span = min(Ts * mlm_prob // 3, 50)
+        m = random_spans_noise_mask(Ts, mlm_prob, span)
+        return (torch.from_numpy(m).to(dev).unsqueeze(0).expand(B, Ts) & valid.bool()).contiguous(), None
     if span_boundary is not None:
         # inference: the given frame ranges are the mask (collate_fn.py:364-366); encode them as
-        # pseudo-phones so that the same kernel expands them
+        # pseudo-phones so that the same kernel expands them.  zip(s[::2], s[1::2]) drops an odd trailing entry.
         sb = [list(map(int, (s.tolist() if hasattr(s, "tolist") else s))) for s in span_boundary]
         n = max(len(s) // 2 for s in sb)
         pm = np.zeros((B, max(n, 1)), dtype=np.uint8)
@@ -87,14 +95,9 @@ def phones_masking(xs_pad, src_mask, align_start, align_end, align_start_lengths
         ln = np.zeros((B,), dtype=np.int64)
         for b, s in enumerate(sb):
             k = len(s) // 2
-            pm[b, :k], st_[b, :k], en_[b, :k], ln[b] = 1, s[0::2], s[1::2], k
+            pm[b, :k], st_[b, :k], en_[b, :k], ln[b] = 1, s[0::2][:k], s[1::2][:k], k
         pm_d, a_s, a_e, lens = (torch.from_numpy(x).to(dev) for x in (pm, st_, en_, ln))
         Tt = pm.shape[1]
-    elif mean_phn_span == 0:
-        # speech-only batches (collate_fn.py:357-361): one frame-level draw shared by the batch
-        span = min(Ts * mlm_prob // 3, 50)
-        m = random_spans_noise_mask(Ts, mlm_prob, span)
-        return (torch.from_numpy(m).to(dev).unsqueeze(0).expand(B, Ts) & valid.bool()).contiguous(), None
     else:
         pm = draw_phone_masks(align_start_lengths.tolist(), mlm_prob, mean_phn_span, Tt)
         pm_d = torch.from_numpy(pm).to(dev)
@@ -158,20 +161,31 @@ class MLMCollateFn:
             if key not in self.not_sequence:
                 out[key + "_lengths"] = torch.tensor([d[key].shape[0] for d in data], dtype=torch.long)
         feats, feats_lengths = self.feats_extract(out["speech"].to(dev), out["speech_lengths"].to(dev))
-        text, text_lengths = out["text"].to(dev), out["text_lengths"]
-        fs, hop = self.feats_extract.fs, self.feats_extract.hop_length
-        a_s = align_to_frames(out["align_start"].to(dev), fs, hop)
-        a_e = align_to_frames(out["align_end"].to(dev), fs, hop)
-        a_len = out["align_start_lengths"]
+        mlm_prob, mean_phn_span, sega_emb = self.mlm_prob, self.mean_phn_span, self.sega_emb
+        if "text" not in out:
+            # speech-only batches (collate_fn.py:222-233): a one-token dummy text (-2), no alignment, one
+            # frame-level span draw shared by the batch with mlm_prob 0.15, no segment ids
+            text = torch.zeros_like(feats_lengths.unsqueeze(-1)) - 2
+            text_lengths = (torch.zeros_like(feats_lengths) + 1).cpu()
+            a_s = torch.zeros(text.shape, dtype=torch.int32, device=dev)
+            a_e = torch.zeros(text.shape, dtype=torch.int32, device=dev)
+            a_len = torch.zeros_like(feats_lengths).cpu()
+            sega_emb, mean_phn_span, mlm_prob = False, 0, 0.15
+        else:
+            text, text_lengths = out["text"].to(dev), out["text_lengths"]
+            fs, hop = self.feats_extract.fs, self.feats_extract.hop_length
+            a_s = align_to_frames(out["align_start"].to(dev), fs, hop)
+            a_e = align_to_frames(out["align_end"].to(dev), fs, hop)
+            a_len = out["align_start_lengths"]
         max_slen = int(feats_lengths.max().item())
         speech_pad = feats[:, :max_slen].contiguous()
         ar_t = torch.arange(text.shape[1], device=dev)
         text_mask = (ar_t[None, :] < text_lengths.to(dev)[:, None]).unsqueeze(-2)
         speech_mask = (torch.arange(max_slen, device=dev)[None, :] < feats_lengths[:, None]).unsqueeze(-2)
         span_boundary = out.get("span_boundary")
-        masked_position, _ = phones_masking(speech_pad, speech_mask, a_s, a_e, a_len, self.mlm_prob,
-                                            self.mean_phn_span, span_boundary)
-        sseg, tseg = get_segment_pos(speech_pad, text, a_s, a_e, a_len, self.sega_emb)
+        masked_position, _ = phones_masking(speech_pad, speech_mask, a_s, a_e, a_len, mlm_prob, mean_phn_span,
+                                            span_boundary)
+        sseg, tseg = get_segment_pos(speech_pad, text, a_s, a_e, a_len, sega_emb)
         return uttids, dict(speech=speech_pad, text=text, masked_position=masked_position, speech_mask=speech_mask,
                             text_mask=text_mask, speech_segment_pos=sseg, text_segment_pos=tseg,
                             speech_lengths=out["speech_lengths"], text_lengths=text_lengths)

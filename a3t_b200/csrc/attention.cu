@@ -499,7 +499,7 @@ extern "C" int a3t_relpos_softmax_fwd(const void* ac, const void* bd_raw, int dt
   const bool v4 = (S % 4) == 0 && (ld % 4) == 0 &&
                   ((((uintptr_t)ac | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)keymask) & 15) == 0);
   if (v4 && dtype_p == A3T_BF16 && dtype_in == A3T_BF16 && S <= 2048 && (((uintptr_t)bd_raw & 15) == 0) &&
-      !getenv("A3T_SOFTMAX_SMEM")) {
+      !tune_env("A3T_SOFTMAX_SMEM")) {
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;
 #define A3T_SM_FWD_REG(NIT, FULL)                                                                               \
@@ -577,7 +577,7 @@ extern "C" int a3t_relpos_softmax_bwd(const void* dPd, int dtype_in, const void*
   A3T_REQUIRE(dtype_in == A3T_F32 || dtype_in == A3T_BF16, "relpos_softmax_bwd: bad input dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_in == A3T_BF16 && dtype_p == A3T_BF16 && dtype_o == A3T_BF16 && (S % 4) == 0 && (ld % 4) == 0 && S <= 2048 &&
-      ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0) && !getenv("A3T_SOFTMAX_SMEM")) {
+      ((((uintptr_t)dPd | (uintptr_t)P | (uintptr_t)dS) & 15) == 0) && !tune_env("A3T_SOFTMAX_SMEM")) {
     const int64_t nrows = (int64_t)B * H * S;
     int rb = (int)((nrows + 7) / 8);
     if (rb > 148 * 2 * 8) rb = 148 * 2 * 8;

@@ -121,6 +121,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Tuning / experiment switches (A3T_TC_*, A3T_SOFTMAX_SMEM ...) exist only in builds made with -DA3T_TUNING
+// (`make TUNING=1`); the release library never reads the environment.
+#ifdef A3T_TUNING
+#include <stdlib.h>
+static inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tune_env(const char*) { return nullptr; }
+#endif
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace a3t

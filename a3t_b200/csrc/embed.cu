@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) embed_assemble_fwd_kernel(
     const float* __restrict__ speech_y, const int64_t* __restrict__ text, const int64_t* __restrict__ sseg,
     const int64_t* __restrict__ tseg, const float* __restrict__ emb, const float* __restrict__ seg,
     float* __restrict__ xs, int B, int Ts, int Tt, int D, float xscale, float drop_p,
-    const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text) {
+    const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text, int V, int nseg,
+    int* __restrict__ err) {
   A3T_PDL_TRIGGER();
   Drop ds = make_drop(drop_p, seed, site_speech);
   Drop dt = make_drop(drop_p, seed, site_text);
@@ -44,13 +45,24 @@ __global__ void __launch_bounds__(256) embed_assemble_fwd_kernel(
     if (s < Ts) {
       int64_t li = ((int64_t)b * Ts + s) * D + d;
       v = drop_apply(ds, (unsigned long long)li, speech_y[li]);
-      if (sseg) v += seg[sseg[(int64_t)b * Ts + s] * D + d];
+      if (sseg) {
+        const int64_t id = sseg[(int64_t)b * Ts + s];
+        if (id >= 0 && id < nseg) v += seg[id * D + d];
+        else if (err && d == 0) atomicOr(err, 2);  // torch raises IndexError here: flag it, add nothing
+      }
     } else {
       int j = s - Ts;
       int64_t li = ((int64_t)b * Tt + j) * D + d;
       int64_t tok = text[(int64_t)b * Tt + j];
-      v = drop_apply(dt, (unsigned long long)li, emb[tok * D + d] * xscale);
-      if (tseg) v += seg[tseg[(int64_t)b * Tt + j] * D + d];
+      float e = 0.f;
+      if (tok >= 0 && tok < V) e = emb[tok * D + d];
+      else if (err && d == 0) atomicOr(err, 1);
+      v = drop_apply(dt, (unsigned long long)li, e * xscale);
+      if (tseg) {
+        const int64_t id = tseg[(int64_t)b * Tt + j];
+        if (id >= 0 && id < nseg) v += seg[id * D + d];
+        else if (err && d == 0) atomicOr(err, 2);
+      }
     }
     xs[i] = v;
   }
@@ -60,7 +72,8 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(
     const float* __restrict__ dxs, const int64_t* __restrict__ text, const int64_t* __restrict__ sseg,
     const int64_t* __restrict__ tseg, float* __restrict__ dspeech_y, float* __restrict__ demb,
     float* __restrict__ dseg, int B, int Ts, int Tt, int D, float xscale, int emb_pad, int seg_pad,
-    float drop_p, const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text) {
+    float drop_p, const unsigned long long* __restrict__ seed, uint32_t site_speech, uint32_t site_text, int V,
+    int nseg) {
   A3T_PDL_TRIGGER();
   Drop ds = make_drop(drop_p, seed, site_speech);
   Drop dt = make_drop(drop_p, seed, site_text);
@@ -78,16 +91,16 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(
       dspeech_y[li] = drop_apply(ds, (unsigned long long)li, g);
       if (sseg && dseg) {
         int64_t id = sseg[(int64_t)b * Ts + s];
-        if (id != seg_pad) atomicAdd(&dseg[id * D + d], g);
+        if (id != seg_pad && id >= 0 && id < nseg) atomicAdd(&dseg[id * D + d], g);
       }
     } else {
       int j = s - Ts;
       int64_t li = ((int64_t)b * Tt + j) * D + d;
       int64_t tok = text[(int64_t)b * Tt + j];
-      if (demb && tok != emb_pad) atomicAdd(&demb[tok * D + d], drop_apply(dt, (unsigned long long)li, g) * xscale);
+      if (demb && tok != emb_pad && tok >= 0 && tok < V) atomicAdd(&demb[tok * D + d], drop_apply(dt, (unsigned long long)li, g) * xscale);
       if (tseg && dseg) {
         int64_t id = tseg[(int64_t)b * Tt + j];
-        if (id != seg_pad) atomicAdd(&dseg[id * D + d], g);
+        if (id != seg_pad && id >= 0 && id < nseg) atomicAdd(&dseg[id * D + d], g);
       }
     }
   }
@@ -122,14 +135,15 @@ extern "C" int a3t_embed_assemble_fwd(const float* speech_y, const int64_t* text
                                       const int64_t* tseg, const float* emb, const float* seg, float* xs, int B,
                                       int Ts, int Tt, int D, float xscale, float drop_p,
                                       const unsigned long long* seed, uint32_t site_speech, uint32_t site_text,
-                                      void* stream) {
+                                      int V, int nseg, int* err_flag, void* stream) {
   A3T_REQUIRE(speech_y && xs && (Tt == 0 || (text && emb)), "embed_assemble_fwd: null pointer");
   A3T_REQUIRE((sseg == nullptr && tseg == nullptr) || seg, "embed_assemble_fwd: segment ids without table");
   A3T_REQUIRE(drop_p == 0.f || seed, "embed_assemble_fwd: dropout needs a seed");
   int64_t n = (int64_t)B * (Ts + Tt) * D;
   if (n == 0) return A3T_OK;
   embed_assemble_fwd_kernel<<<ew_blocks2(n), 256, 0, (cudaStream_t)stream>>>(
-      speech_y, text, sseg, tseg, emb, seg, xs, B, Ts, Tt, D, xscale, drop_p, seed, site_speech, site_text);
+      speech_y, text, sseg, tseg, emb, seg, xs, B, Ts, Tt, D, xscale, drop_p, seed, site_speech, site_text, V, nseg,
+      err_flag);
   return check_launch("embed_assemble_fwd");
 }
 
@@ -137,13 +151,13 @@ extern "C" int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, con
                                       float* dspeech_y, float* demb, float* dseg, int B, int Ts, int Tt, int D,
                                       float xscale, int emb_pad, int seg_pad, float drop_p,
                                       const unsigned long long* seed, uint32_t site_speech, uint32_t site_text,
-                                      void* stream) {
+                                      int V, int nseg, void* stream) {
   A3T_REQUIRE(dxs && dspeech_y, "embed_assemble_bwd: null pointer");
   A3T_REQUIRE(drop_p == 0.f || seed, "embed_assemble_bwd: dropout needs a seed");
   int64_t n = (int64_t)B * (Ts + Tt) * D;
   if (n == 0) return A3T_OK;
   embed_assemble_bwd_kernel<<<ew_blocks2(n), 256, 0, (cudaStream_t)stream>>>(
       dxs, text, sseg, tseg, dspeech_y, demb, dseg, B, Ts, Tt, D, xscale, emb_pad, seg_pad, drop_p, seed, site_speech,
-      site_text);
+      site_text, V, nseg);
   return check_launch("embed_assemble_bwd");
 }

@@ -13,6 +13,16 @@ int gemm_tc_launch(const A3tGemmDesc* d, const void* A, const void* B, void* C, 
 
 using namespace a3t;
 
+// bf16 problems that A3T_IMPL_AUTO handed to the CUDA-core kernel because they did not qualify for the
+// tcgen05 one (a silent 5x slowdown when it happens on a hot shape): counted so callers can assert on it
+static unsigned long long g_auto_fallbacks = 0;
+
+extern "C" int a3t_gemm_fallback_count(int reset) {
+  const unsigned long long n = __atomic_load_n(&g_auto_fallbacks, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_auto_fallbacks, 0ull, __ATOMIC_RELAXED);
+  return n > 0x7fffffffull ? 0x7fffffff : (int)n;
+}
+
 extern "C" int a3t_gemm(const A3tGemmDesc* d, const void* A, const void* B, void* C, const float* bias,
                         const float* res, const void* mask, const unsigned long long* seed, void* stream) {
   A3T_REQUIRE(d && A && B && C, "gemm: null pointer");
@@ -35,11 +45,12 @@ extern "C" int a3t_gemm(const A3tGemmDesc* d, const void* A, const void* B, void
   if (d->impl != A3T_IMPL_SIMT) {
     int rc = gemm_tc_launch(d, A, B, C, bias, res, mask, seed, st, false);
     if (rc != A3T_ERR_UNSUPPORTED) return rc;
-    if (d->impl == A3T_IMPL_TC) {
+    if (d->impl == A3T_IMPL_TC || d->impl == A3T_IMPL_TC_PAIR) {
       set_error("gemm: problem does not qualify for the tcgen05 kernel (M=%d N=%d K=%d mode=%d)", d->M, d->N, d->K,
                 d->mode);
       return A3T_ERR_UNSUPPORTED;
     }
+    if (d->dtype_a == A3T_BF16 && d->dtype_b == A3T_BF16) __atomic_fetch_add(&g_auto_fallbacks, 1ull, __ATOMIC_RELAXED);
   }
   return gemm_simt_launch(d, A, B, C, bias, res, mask, seed, st);
 }

@@ -422,7 +422,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const A3tGemmDesc& d = p.d;
 
+#ifdef A3T_TUNING
   const int dbg = p.dbg;
+#else
+  constexpr int dbg = 0;  // timing-experiment modes (garbage results) exist in -DA3T_TUNING builds only
+#endif
   if (warp == PRODUCER_WARP) {
     // ===================================== TMA producer =====================================
     // The K loop is one thread issuing dependent instructions: it is kept to a barrier wait, the TMA
@@ -970,7 +974,7 @@ static int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
-    if (const char* e = getenv("A3T_TC_SMS")) {  // tuning experiments: restrict the persistent grid
+    if (const char* e = tune_env("A3T_TC_SMS")) {  // tuning experiments: restrict the persistent grid
       int v = atoi(e);
       if (v >= 2 && v < n) n = v;
     }
@@ -1057,10 +1061,13 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   const bool can_split = d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && d.sc_tap == 1 &&
                          d.sc_n == d.taps && d.sc_m == (int64_t)d.taps * d.cin;
   // WGRAD through TMA store / reduce-add: output rows are contiguous (c, tap) runs of fp32
-  const char* env_cta = getenv("A3T_TC_CTA");  // "1" / "2": force single-CTA / CTA-pair tiles (experiments)
-  const bool force_pair = env_cta && atoi(env_cta) == 2;
+  // 0 = cost model decides; 1 / 2 = force single-CTA / CTA-pair tiles (d.impl == A3T_IMPL_TC_PAIR, or the
+  // A3T_TC_CTA switch of tuning builds)
+  const char* env_cta = tune_env("A3T_TC_CTA");
+  const int cta_force = env_cta ? atoi(env_cta) : (d.impl == A3T_IMPL_TC_PAIR ? 2 : 0);
+  const bool force_pair = cta_force == 2;
   const bool wg_tma = can_split && (d.taps == 1 || (d.taps == 3 && !force_pair)) && ((int64_t)d.cin * d.taps) % 4 == 0 &&
-                      al16(C) && !getenv("A3T_TC_GENERIC_EPI") && !getenv("A3T_TC_WGRAD_ATOMIC");
+                      al16(C) && !tune_env("A3T_TC_GENERIC_EPI") && !tune_env("A3T_TC_WGRAD_ATOMIC");
   const bool wg3 = wg_tma && d.taps == 3;  // N tile = 3 taps x 64 channels (single-CTA tiles only)
   int best_bn = 0, best_split = 1, best_cta2 = 0;
   double best_cost = 1e30;
@@ -1070,7 +1077,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     // SM) gain 2-6 % on the K >= 1152 implicit-conv shapes (FFN fwd / dgrad) and lose on the small-K, batched and
     // weight-gradient shapes, so they are the default for 3-tap convolutions only
     const bool pair_default = d.mode == A3T_GEMM_CONV && d.taps >= 3 && d.K >= 1024 && p.m_tiles >= 8;
-    if (env_cta ? atoi(env_cta) != cta2 + 1 : (cta2 != 0) != pair_default) continue;
+    if (cta_force ? cta_force != cta2 + 1 : (cta2 != 0) != pair_default) continue;
     if (cta2 && p.m_tiles < 2) continue;
     if (cta2 && wg3) continue;
     for (int ci = 0; ci < 5; ci++) {
@@ -1096,7 +1103,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
   }
   if (best_bn == 0) return A3T_ERR_UNSUPPORTED;
-  if (const char* e = getenv("A3T_TC_BN")) {  // tuning experiments only
+  if (const char* e = tune_env("A3T_TC_BN")) {  // tuning experiments only
     int v = atoi(e);
     if (v >= 16 && v <= 256 && v % 16 == 0 && !(p.b_mn && v % (best_cta2 ? 128 : 64)) && !(best_cta2 && v % 32)) {
       if (!wg3) {
@@ -1125,7 +1132,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   const int epi_bytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
   p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes - epi_bytes) / (int)stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  if (const char* e = getenv("A3T_TC_STAGES")) {
+  if (const char* e = tune_env("A3T_TC_STAGES")) {
     int v = atoi(e);
     if (v >= 2 && v < p.stages) p.stages = v;
   }
@@ -1156,9 +1163,9 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     if (encode_map(&tmC, C, cdims, cstr, cbox, 4)) epi = EPI_WGRAD_TMA;
   }
   if (epi >= 0) {
-  } else if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && !wg3 && !getenv("A3T_TC_GENERIC_EPI")) epi = EPI_WGRAD;
+  } else if (d.mode == A3T_GEMM_WGRAD && d.dtype_c == A3T_F32 && plain_epi && !wg3 && !tune_env("A3T_TC_GENERIC_EPI")) epi = EPI_WGRAD;
   else if (d.mode != A3T_GEMM_WGRAD && p.splits == 1 && p.vec_c && (!res || (p.vec_r && d.dtype_c == A3T_F32)) &&
-           (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !getenv("A3T_TC_GENERIC_EPI")) {
+           (!mask || (p.vec_m && d.dtype_mask == A3T_BF16)) && (d.N % 4) == 0 && !tune_env("A3T_TC_GENERIC_EPI")) {
     // TMA tensor store of C: (N, rows, batch2 | sequence, batch1); superchunks must not straddle N tiles
     const int sc_cols = d.dtype_c == A3T_BF16 ? 64 : 32;
     const int cs = d.dtype_c == A3T_BF16 ? 2 : 4;
@@ -1214,8 +1221,8 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
       return A3T_ERR_CUDA;
     }
   }
-  if (const char* e = getenv("A3T_TC_DBGMODE")) p.dbg = atoi(e);
-  if (getenv("A3T_TC_DEBUG"))
+  if (const char* e = tune_env("A3T_TC_DBGMODE")) p.dbg = atoi(e);
+  if (tune_env("A3T_TC_DEBUG"))
     fprintf(stderr, "gemm_tc: M=%d N=%d K=%d mode=%d cta2=%d bn=%d splits=%d stages=%d work=%d epi=%d\n", d.M, d.N, d.K,
             d.mode, (int)cta2, p.block_n, p.splits, p.stages, p.num_work, epi);
   cudaLaunchConfig_t cfg;
@@ -1234,7 +1241,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   } else {
     cfg.gridDim = dim3(p.num_work < sms ? p.num_work : sms);
   }
-  static const bool pdl = !getenv("A3T_NO_PDL");
+  static const bool pdl = !tune_env("A3T_NO_PDL");
   if (pdl && !(p.splits > 1 && !d.c_zeroed)) {  // (the library's own memset node must not be overtaken)
     attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[nattr].val.programmaticStreamSerializationAllowed = 1;

@@ -73,6 +73,9 @@ class WeightCache:
 
     def __init__(self):
         self._c = {}
+        # bumped whenever an entry is (re)built or the cache is dropped: holders of derived state (the trainer's
+        # in-place repack plan) compare it to know their pointers are stale
+        self.generation = 0
 
     def packed(self, ops, key, tensors, make):
         sig = tuple((t.data_ptr(), t._version) for t in tensors) + (str(ops.act_dtype),)
@@ -83,10 +86,12 @@ class WeightCache:
             raise RuntimeError(f"weight cache miss for {key} during backward (parameter changed since forward?)")
         val = make()
         self._c[key] = (sig, val)
+        self.generation += 1
         return val
 
     def clear(self):
         self._c.clear()
+        self.generation += 1
 
 
 class _Sites:
@@ -339,7 +344,7 @@ def forward(ops, P: Dict[str, torch.Tensor], wc: WeightCache, cfg: A3TConfig, ba
             need_loss: bool = True):
     """Returns (loss[1] or None, before (B,Ts,odim), after (B,Ts,odim), ctx)."""
     speech = batch["speech"].contiguous()
-    text = batch["text"].contiguous()
+    text = batch["text"].long().contiguous()   # the embedding kernels read int64 ids
     masked = batch["masked_position"].contiguous()
     Bn, Ts, _ = speech.shape
     Tt = text.shape[1]
@@ -347,8 +352,8 @@ def forward(ops, P: Dict[str, torch.Tensor], wc: WeightCache, cfg: A3TConfig, ba
     D = cfg.D
     dev = speech.device
     keymask = torch.cat([batch["speech_mask"].reshape(Bn, Ts), batch["text_mask"].reshape(Bn, Tt)], dim=1).contiguous()
-    sseg = batch["speech_segment_pos"].contiguous() if cfg.sega else None
-    tseg = batch["text_segment_pos"].contiguous() if cfg.sega else None
+    sseg = batch["speech_segment_pos"].long().contiguous() if cfg.sega else None
+    tseg = batch["text_segment_pos"].long().contiguous() if cfg.sega else None
     xscale = math.sqrt(D)
     sites = _Sites()
     ctx = StepContext(training=training)

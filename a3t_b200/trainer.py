@@ -59,7 +59,8 @@ class DataParallelTrainer:
         self.ops = ops if ops is not None else model._backend(dev)
         self._update_fn = update_fn
         self.stats = self.flat_g[self.n:]
-        self._plan, self._plan_tried, self._qkv4 = None, False, []
+        self._plan, self._plan_gen, self._qkv4 = None, -1, []
+        self.in_place_repack = True  # False: drop the packed-weight cache after every step (lazy per-weight re-pack)
         self._rest = None
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -102,10 +103,19 @@ class DataParallelTrainer:
     def _refresh_packed_weights(self, P, wc):
         """The bf16 GEMM operand copies of every weight are rewritten IN PLACE by one batched kernel (the
         parameters live at fixed addresses inside `flat_p`), so the weight cache stays valid and the next
-        step launches no per-weight packing kernels.  Falls back to dropping the cache (lazy re-pack)."""
+        step launches no per-weight packing kernels.  Falls back to dropping the cache (lazy re-pack).
+
+        The plan holds raw pointers to the cache's bf16 buffers, so it is rebuilt whenever the cache rebuilt an
+        entry since the plan was made (`load_state_dict` / checkpoint resume / any in-place torch write bumps the
+        parameter version -> cache miss -> new buffers -> `wc.generation` changes)."""
         ops = self.ops
-        if not self._plan_tried:
-            self._plan_tried = True
+        if not self.in_place_repack:
+            self._plan = None
+            wc.clear()
+            return
+        if self._plan_gen != wc.generation:
+            self._plan_gen = wc.generation
+            self._plan, self._qkv4 = None, []
             entries, qkv4 = [], []
             for key, (_, val) in wc._c.items():
                 if key.endswith(".qkv4"):

@@ -48,6 +48,7 @@ extern "C" {
 #define A3T_IMPL_AUTO 0    /* tcgen05 tensor-core kernel when the shape/dtype qualifies, else SIMT  */
 #define A3T_IMPL_SIMT 1    /* force the fp32-accumulate CUDA-core kernel (exact-fp32 parity mode)   */
 #define A3T_IMPL_TC 2      /* force tcgen05 (error if the problem does not qualify)                 */
+#define A3T_IMPL_TC_PAIR 3 /* as A3T_IMPL_TC, and force cta_group::2 tiles (256 x N on a CTA pair)      */
 
 const char* a3t_last_error(void);
 int a3t_version(void);
@@ -93,6 +94,9 @@ int a3t_gemm(const A3tGemmDesc* d, const void* A, const void* B, void* C, const 
 /* 1 if a3t_gemm would run this problem on the tcgen05 tensor-core kernel (shape, dtype, stride and
  * alignment rules of gemm_tc.cu), 0 if it would take the CUDA-core kernel.  No launch. */
 int a3t_gemm_tc_supported(const A3tGemmDesc* d, const void* A, const void* B, void* C);
+/* Number of bf16 x bf16 problems A3T_IMPL_AUTO has handed to the CUDA-core kernel since the library was
+ * loaded (or since the last call with reset != 0).  A hot path asserts this stays 0. */
+int a3t_gemm_fallback_count(int reset);
 
 /* Pack an fp32 conv/linear weight (N, C, taps) into bf16 K-major operands for the tensor-core
  * kernels: fwd[n, tap*C + c] = w[n,c,tap];  dgrad[c, tap'*N + n] = w[n,c,taps-1-tap'] (either may
@@ -166,17 +170,20 @@ int a3t_mask_input_bwd(const float* dx, const uint8_t* masked, float* dmask_feat
  *   xs[b, t<Ts]   = dropout(speech_y[b,t]) + seg[sseg[b,t]]
  *   xs[b, Ts+j]   = dropout(emb[text[b,j]] * xscale) + seg[tseg[b,j]]          xs: (B, Ts+Tt, D) fp32
  * bwd: dspeech_y = keep * dxs[:, :Ts]; demb/dseg += scatter (atomicAdd into zero-initialised
- * buffers; rows `emb_pad` / `seg_pad` (torch padding_idx) receive no gradient). */
+ * buffers; rows `emb_pad` / `seg_pad` (torch padding_idx) receive no gradient).
+ * V / nseg: table sizes.  An id outside [0, V) / [0, nseg) (torch raises IndexError) reads as a zero
+ * row, receives no gradient and sets bit 0 (token) / bit 1 (segment) of *err_flag (device int, may
+ * be NULL) so the host can raise without a per-call synchronisation. */
 int a3t_embed_assemble_fwd(const float* speech_y, const int64_t* text, const int64_t* sseg,
                            const int64_t* tseg, const float* emb, const float* seg, float* xs,
                            int B, int Ts, int Tt, int D, float xscale, float drop_p,
                            const unsigned long long* seed, uint32_t site_speech, uint32_t site_text,
-                           void* stream);
+                           int V, int nseg, int* err_flag, void* stream);
 int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, const int64_t* sseg,
                            const int64_t* tseg, float* dspeech_y, float* demb, float* dseg, int B,
                            int Ts, int Tt, int D, float xscale, int emb_pad, int seg_pad,
                            float drop_p, const unsigned long long* seed, uint32_t site_speech,
-                           uint32_t site_text, void* stream);
+                           uint32_t site_text, int V, int nseg, void* stream);
 
 /* Legacy relative-position masked softmax (transformer/attention.py:145-165 rel_shift, :205-207
  * scale, :79-86 finfo.min fill / softmax / zero fill, :88 dropout).

@@ -154,9 +154,111 @@ def pwg_fixture():
     print("pwg:", tuple(y.shape), float(y.abs().mean()))
 
 
+def model_d384_fixture():
+    """Paper WIDTH (D=384, H=2, FF=1536, dw 7/31, postnet 5x256) with 1+1 blocks, B=2, Ts=1024, Tt=128, ragged.
+    Weights come from `fixtures.fill_params(seed)` (regenerated by the tests), outputs from the reference."""
+    from oracle.fixtures import fill_params, grad_probe
+
+    conf = R.model_conf("paper")
+    conf["encoder_conf"].update(num_blocks=1)
+    conf["decoder_conf"].update(num_blocks=1)
+    vocab, wseed = 73, 20241
+    ref = R.build_reference_model(conf, vocab=vocab, dropout_zero=True)
+    fill_params(ref, wseed)
+    batch, aux = R.synthetic_batch(2, 1024, 128, vocab=vocab, seed=5, ragged=True)
+    # make the second utterance clearly shorter (padded keys + padded frames at the paper shape)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    ref.train()
+    ref.zero_grad(set_to_none=True)
+    loss, stats, weight = ref(**batch)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    bn_after = {k: v.clone() for k, v in ref.state_dict().items() if "running" in k}
+    ref.load_state_dict(sd0)
+    ref.eval()
+    with torch.no_grad():
+        before_e, after_e, _, _ = ref._forward(
+            dict(speech_pad=batch["speech"], text_pad=batch["text"], masked_position=batch["masked_position"],
+                 speech_mask=batch["speech_mask"], text_mask=batch["text_mask"],
+                 speech_segment_pos=batch["speech_segment_pos"], text_segment_pos=batch["text_segment_pos"]),
+            batch["speech_segment_pos"])
+        loss_e, _, _ = ref(**batch)
+    small = {k: v for k, v in batch.items() if k != "speech"}   # speech is regenerated: randn under manual_seed(5)
+    torch.save(dict(conf=conf, vocab=vocab, weight_seed=wseed, batch_seed=5, batch_small=small,
+                    speech_lengths=batch["speech_lengths"], speech_probe=batch["speech"][:, ::97, ::7].clone(),
+                    loss_train=loss.detach(), loss_eval=loss_e,
+                    grad_norm={n: float(g.norm()) for n, g in grads.items()},
+                    grad_probe={n: grad_probe(g) for n, g in grads.items()},
+                    bn_after_probe={k: v.reshape(-1)[:16].clone() for k, v in bn_after.items()},
+                    before_eval=before_e[:, ::8].clone(), after_eval=after_e[:, ::8].clone()),
+               os.path.join(OUT, "model_d384.pt"))
+    print("model_d384: loss_train", float(loss), "loss_eval", float(loss_e), "params",
+          sum(p.numel() for p in ref.parameters()))
+
+
+def pwg30_fixture():
+    """The published generator shape: 30 layers / 3 stacks (dilations 1..512), 200 frames -> 60 000 samples."""
+    R._activate()
+    from espnet2.gan_tts.parallel_wavegan import ParallelWaveGANGenerator
+    from oracle.fixtures import fill_params
+
+    torch.manual_seed(4)
+    gen = ParallelWaveGANGenerator(layers=30, stacks=3, upsample_params={"upsample_scales": [4, 5, 3, 5]})
+    gen.remove_weight_norm()
+    gen.eval()
+    fill_params(gen, 77, scale=0.8)
+    g = torch.Generator().manual_seed(10)
+    c = torch.randn(1, 80, 200, generator=g)
+    z = torch.randn(1, 1, 200 * 300, generator=g)
+    with torch.no_grad():
+        y = gen(c, z)
+    torch.save(dict(layers=30, stacks=3, scales=[4, 5, 3, 5], weight_seed=77, weight_scale=0.8,
+                    param_shapes={k: tuple(v.shape) for k, v in gen.state_dict().items()},
+                    c=c, z_seed=10, z_probe=z[0, 0, ::601].clone(), wav=y.clone()), os.path.join(OUT, "pwg30.pt"))
+    print("pwg30:", tuple(y.shape), float(y.abs().mean()), float(y.abs().max()))
+
+
+def collate_fixture():
+    """`mlm_collate_fn` end to end (espnet2/train/collate_fn.py:158-287) on raw utterances: text+alignment batch,
+    the span_boundary (inference) batch and the speech-only batch."""
+    R._activate()
+    from espnet2.train.collate_fn import mlm_collate_fn
+    from espnet2.tts.feats_extract.log_mel_fbank import LogMelFbank
+
+    kw = dict(fs=24000, n_fft=2048, win_length=1200, hop_length=300, fmin=80, fmax=7600, n_mels=80)
+    fe = LogMelFbank(**kw)
+    rng = np.random.RandomState(3)
+    data = []
+    for i, (n, L) in enumerate(((9100, 11), (6400, 7), (7777, 2), (5000, 1))):
+        wav = (0.1 * rng.randn(n)).astype(np.float32)
+        cuts = np.sort(rng.rand(L + 1)) * (n / 24000.0)
+        data.append((f"utt{i}", dict(speech=wav, text=rng.randint(2, 70, size=L).astype(np.int64),
+                                     align_start=cuts[:-1].astype(np.float32), align_end=cuts[1:].astype(np.float32))))
+    out = {"kw": kw, "data": data}
+    np.random.seed(21)
+    with torch.no_grad():
+        out["train"] = mlm_collate_fn(data, float_pad_value=0.0, int_pad_value=0, mlm_prob=0.8, mean_phn_span=8,
+                                      feats_extract=fe, sega_emb=True)
+    sb_data = [(u, dict(d, span_boundary=np.array(sb, dtype=np.int64)))
+               for (u, d), sb in zip(data, ([3, 9], [0, 15], [10, 20], [5, 5]))]
+    np.random.seed(22)
+    with torch.no_grad():
+        out["span_boundary"] = mlm_collate_fn(sb_data, float_pad_value=0.0, int_pad_value=0, mlm_prob=0.8,
+                                              mean_phn_span=8, feats_extract=fe, sega_emb=True)
+    so_data = [(u, dict(speech=d["speech"])) for u, d in data]
+    np.random.seed(23)
+    with torch.no_grad():
+        out["speech_only"] = mlm_collate_fn(so_data, float_pad_value=0.0, int_pad_value=0, mlm_prob=0.8,
+                                            mean_phn_span=8, feats_extract=fe, sega_emb=True)
+    out["seeds"] = dict(train=21, span_boundary=22, speech_only=23)
+    torch.save(out, os.path.join(OUT, "collate.pt"))
+    print("collate:", {k: {kk: tuple(vv.shape) for kk, vv in out[k][1].items()} for k in ("train", "span_boundary", "speech_only")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    model_fixture()
-    kat_fixture()
-    frontend_fixture()
-    pwg_fixture()
+    which = set(sys.argv[1:]) or {"model", "kat", "frontend", "pwg", "d384", "pwg30", "collate"}
+    for name, fn in (("model", model_fixture), ("kat", kat_fixture), ("frontend", frontend_fixture), ("pwg", pwg_fixture),
+                     ("d384", model_d384_fixture), ("pwg30", pwg30_fixture), ("collate", collate_fixture)):
+        if name in which:
+            fn()

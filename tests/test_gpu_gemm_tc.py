@@ -130,11 +130,13 @@ def test_tc_is_what_auto_picks(cuda_lib):
 
 
 @pytest.mark.parametrize("taps,C,N,S,B", [(3, 384, 1536, 1152, 2), (1, 384, 384, 1152, 3), (5, 80, 256, 200, 3)])
-def test_cta_pair_mode(bes, monkeypatch, taps, C, N, S, B):
-    """cta_group::2 (256 x N tiles on a CTA pair, opt-in through A3T_TC_CTA=2): same results as the
-    single-CTA kernel, including an odd number of M tiles (phantom second tile) and split-K wgrad."""
-    tc, simt = bes
-    monkeypatch.setenv("A3T_TC_CTA", "2")
+def test_cta_pair_mode(bes, taps, C, N, S, B):
+    """cta_group::2 (256 x N tiles on a CTA pair, forced with impl = IMPL_TC_PAIR): same results as the
+    CUDA-core kernel, including an odd number of M tiles (phantom second tile) and split-K wgrad."""
+    from a3t_b200.backend import CudaBackend
+
+    _, simt = bes
+    tc = CudaBackend("cuda:0", torch.bfloat16, seed=1234567, impl=_lib.IMPL_TC_PAIR)
     x = g(B, S, C, seed=11)
     w = g(N, C, taps, seed=12, scale=1.0 / math.sqrt(C * taps), dtype=torch.float32)
     bias = g(N, seed=13, dtype=torch.float32)

@@ -280,7 +280,7 @@ def test_trainer_bf16_in_place_repack_equals_lazy_repack(fx):
     for lazy in (False, True):
         m = _model(fx, torch.bfloat16).train()
         tr = DataParallelTrainer(m, lr=1e-3, warmup=0.0)
-        tr._plan_tried = lazy  # True: never build the plan -> cache dropped every step
+        tr.in_place_repack = not lazy  # lazy: never build the plan -> cache dropped every step
         b = _cuda(fx["batch"])
         ls = []
         for _ in range(4):

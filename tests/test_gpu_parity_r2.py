@@ -1,0 +1,396 @@
+"""Round-2 parity gates (-m gpu): the benchmarked bf16 / tcgen05 path and the fp32 path against fixtures the
+REFERENCE produced at the paper width (tests/golden/model_d384.pt), the 30-layer vocoder, the whole collate
+functor, and the tensor-core GEMM / bf16 element-wise kernels against the CPU oracle (not against another CUDA
+kernel).  Tolerances are written where they are applied."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import _d384
+from a3t_b200 import _lib
+from oracle import a3t_oracle as O
+from oracle.fixtures import fill_params, grad_probe
+from oracle.oracle_backend import OracleBackend
+
+
+def _cuda(b):
+    return {k: v.cuda() for k, v in b.items()}
+
+
+@pytest.fixture(scope="module")
+def d384(golden_dir, cuda_lib):
+    assert torch.cuda.is_available()
+    return _d384.load(golden_dir)
+
+
+# ------------------------------------------------------------------------------------------------
+# model at the paper width against the reference's own numbers
+# ------------------------------------------------------------------------------------------------
+def _grad_errors(m, fx):
+    """worst |probe - ref| / (5e-4 * max|ref| + 5e-5) over parameters, and the minimum probe cosine."""
+    worst, worst_n, cos_min, cos_n = 0.0, "", 1.0, ""
+    for n, p in m.named_parameters():
+        ref = fx["grad_probe"][n]
+        pr = grad_probe(p.grad)
+        sc = float(ref.abs().max())
+        r = float((pr - ref).abs().max()) / (5e-4 * sc + 5e-5)
+        if r > worst:
+            worst, worst_n = r, n
+        if fx["grad_norm"][n] > 1e-4 and not (n.endswith("linear_k.bias") or n.endswith("depthwise_conv.bias")):
+            c = float(torch.nn.functional.cosine_similarity(pr, ref, dim=0))
+            if c < cos_min:
+                cos_min, cos_n = c, n
+    return worst, worst_n, cos_min, cos_n
+
+
+def test_d384_fp32_matches_reference(d384):
+    """fp32 kernels, D=384 / H=2 / FF=1536 / dw 7+31 / postnet 5x256, B=2, Ts=1024, Tt=128 ragged:
+    |loss - ref| <= 1e-4 * |ref| (north-star gate), every gradient probe within 5e-4 of its scale."""
+    fx, b = d384
+    m = _d384.build(fx).cuda().train()
+    loss, _, _ = m(**_cuda(b))
+    ref = float(fx["loss_train"])
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref), (float(loss), ref)
+    loss.backward()
+    worst, worst_n, _, _ = _grad_errors(m, fx)
+    assert worst <= 1.0, (worst_n, worst)
+    for n, p in m.named_parameters():
+        gn = fx["grad_norm"][n]
+        assert abs(float(p.grad.norm()) - gn) <= 1e-3 * gn + 1e-5, n
+    sd = m.state_dict()
+    for k, v in fx["bn_after_probe"].items():
+        assert torch.allclose(sd[k].reshape(-1)[:16].cpu(), v, atol=1e-5, rtol=1e-5), k
+    m.eval()
+    with torch.no_grad():
+        fill_params(m, fx["weight_seed"])   # restore the running statistics the train step moved
+        m.cuda()
+        le, _, _ = m(**_cuda(b))
+        bb = _cuda(b)
+        before, after, _, _ = m._forward(dict(speech_pad=bb["speech"], text_pad=bb["text"],
+                                              masked_position=bb["masked_position"], speech_mask=bb["speech_mask"],
+                                              text_mask=bb["text_mask"], speech_segment_pos=bb["speech_segment_pos"],
+                                              text_segment_pos=bb["text_segment_pos"]))
+    assert abs(float(le) - float(fx["loss_eval"])) <= 1e-4 * abs(float(fx["loss_eval"]))
+    assert torch.allclose(before[:, ::8].cpu(), fx["before_eval"], atol=1e-3, rtol=1e-4)
+    assert torch.allclose(after[:, ::8].cpu(), fx["after_eval"], atol=1e-3, rtol=1e-4)
+
+
+def bf16_parity_numbers(fx, b, impl=_lib.IMPL_TC):
+    """Measured deviation of the bf16 / tcgen05 path from the fp32 reference on the D=384 fixture (also reported
+    by bench.py as the `parity` object)."""
+    m = _d384.build(fx, torch.bfloat16)
+    m.gemm_impl = impl
+    m = m.cuda().train()
+    loss, _, _ = m(**_cuda(b))
+    loss.backward()
+    ref = float(fx["loss_train"])
+    worst, worst_n, cos_min, cos_n = _grad_errors(m, fx)
+    rel_norm = max(abs(float(p.grad.norm()) - fx["grad_norm"][n]) / fx["grad_norm"][n]
+                   for n, p in m.named_parameters() if fx["grad_norm"][n] > 1e-3)
+    return dict(loss=float(loss), loss_ref=ref, loss_rel_err=abs(float(loss) - ref) / abs(ref), grad_probe_cos_min=cos_min,
+                grad_probe_cos_min_param=cos_n, grad_norm_rel_err_max=rel_norm)
+
+
+def test_d384_bf16_tensor_core_path_close_to_reference(d384):
+    """The benchmarked configuration (bf16 GEMM operands, tcgen05, IMPL_TC: no silent fallback) on the same
+    fixture.  The reference has no bf16 path, so this is a measured deviation with a stated bound:
+    loss within 5e-3 relative, every gradient probe cosine > 0.98, gradient norms within 5 %."""
+    fx, b = d384
+    _lib.call("a3t_gemm_fallback_count", 1)
+    r = bf16_parity_numbers(fx, b)
+    print("bf16 parity:", r)
+    assert r["loss_rel_err"] < 5e-3, r
+    assert r["grad_probe_cos_min"] > 0.98, r
+    assert r["grad_norm_rel_err_max"] < 5e-2, r
+    assert _lib.call("a3t_gemm_fallback_count", 0) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# ADVICE round 1
+# ------------------------------------------------------------------------------------------------
+def test_autograd_path_uses_the_forward_seed_in_backward(golden_dir, cuda_lib):
+    """`model(**batch)` advances the master dropout seed before `loss.backward()` runs; the backward must still
+    regenerate the forward's masks.  Compare with graph.forward / graph.backward at a pinned seed (p = 0.2 / 0.5)."""
+    from a3t_b200 import graph
+    from a3t_b200.model import build_model
+
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+    conf = fx["conf"]
+    m = build_model(conf["encoder_conf"], conf["decoder_conf"], conf["model_conf"], vocab_size=fx["vocab"])
+    m.load_state_dict(fx["state_dict"])
+    m = m.cuda().train()
+    b = _cuda(fx["batch"])
+    ops = m._backend(b["speech"].device)
+    ops.set_seed(4242)
+    bn0 = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+    loss, _, _ = m(**b)
+    loss.backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.load_state_dict(bn0, strict=False)
+    ops.set_seed(4242)
+    P = m._param_dict()
+    l2, _, _, ctx = graph.forward(ops, P, m._wcache, m.cfg, b, True, True)
+    G = graph.backward(ops, P, m._wcache, m.cfg, ctx, torch.ones(1, device="cuda"))
+    assert float(loss) == float(l2)
+    for n in got:
+        sc = float(G[n].abs().max())
+        assert float((got[n] - G[n].view(got[n].shape)).abs().max()) <= 1e-5 * sc + 1e-7, n
+
+
+def test_trainer_repack_plan_follows_load_state_dict(golden_dir, cuda_lib):
+    """bf16 trainer: loading new weights after the first step (checkpoint resume) must rebuild the in-place
+    repack plan, otherwise the GEMMs keep reading stale bf16 copies."""
+    from a3t_b200.trainer import DataParallelTrainer
+
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+
+    def mk():
+        from a3t_b200.model import build_model
+        conf = fx["conf"]
+        enc, dec = dict(conf["encoder_conf"]), dict(conf["decoder_conf"])
+        for c in (enc, dec):
+            c.update(dropout_rate=0.0, positional_dropout_rate=0.0, attention_dropout_rate=0.0)
+        m = build_model(enc, dec, conf["model_conf"], vocab_size=fx["vocab"], act_dtype=torch.bfloat16)
+        m.load_state_dict(fx["state_dict"])
+        m.postnet.dropout_rate = 0.0
+        return m.cuda().train()
+
+    b = _cuda(fx["batch"])
+    other = {k: (v * 0.5 if v.dtype.is_floating_point and v.dim() > 1 else v) for k, v in fx["state_dict"].items()}
+    m1 = mk()
+    t1 = DataParallelTrainer(m1, lr=1e-3, warmup=0.0)
+    t1.step(b)
+    t1.step(b)
+    m1.load_state_dict(other)
+    s = t1.step(b)             # first step on the loaded weights (cache miss -> fresh packs)
+    s = t1.step(b).clone()     # second: served by the (rebuilt) in-place plan
+    m2 = mk()
+    m2.load_state_dict(other)
+    t2 = DataParallelTrainer(m2, lr=1e-3, warmup=0.0)
+    t2.flat_m.copy_(t1.flat_m); t2.flat_v.copy_(t1.flat_v)  # not compared: only the loss of the SAME weights matters
+    m2.load_state_dict({k: v for k, v in m1.state_dict().items()})
+    l1 = float(s[0] / s[2])
+    # a fresh model holding m1's current weights must see the same loss on its first step as m1 sees next
+    s_next = t1.step(b)
+    s2 = t2.step(b)
+    assert abs(float(s_next[0] / s_next[2]) - float(s2[0] / s2[2])) <= 2e-3 * abs(float(s2[0] / s2[2])), (l1, float(s2[0] / s2[2]))
+
+
+def test_mask_dtypes_and_id_range(golden_dir, cuda_lib):
+    """Masks given as int64 / float are read as `!= 0` (not as raw bytes); an out-of-table token id is flagged."""
+    from a3t_b200.backend import _u8
+
+    m = torch.tensor([[0, 3, 0, 1]], dtype=torch.int64, device="cuda")
+    assert _u8(m).dtype == torch.uint8 and _u8(m).tolist() == [[0, 1, 0, 1]]
+    assert _u8(m.float()).tolist() == [[0, 1, 0, 1]] and _u8(m.bool()).tolist() == [[0, 1, 0, 1]]
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+    from a3t_b200.model import build_model
+    conf = fx["conf"]
+    mdl = build_model(conf["encoder_conf"], conf["decoder_conf"], conf["model_conf"], vocab_size=fx["vocab"])
+    mdl.load_state_dict(fx["state_dict"])
+    mdl = mdl.cuda().eval()
+    b = _cuda(fx["batch"])
+    with torch.no_grad():
+        l0, _, _ = mdl(**b)
+        b2 = dict(b, masked_position=b["masked_position"].long(), speech_mask=b["speech_mask"].float(),
+                  text_mask=b["text_mask"].int())
+        l1, _, _ = mdl(**b2)
+    assert float(l0) == float(l1)
+    ops = mdl._backend(b["speech"].device)
+    ops.check_ids()
+    bad = dict(b, text=b["text"].clone())
+    bad["text"][0, 0] = fx["vocab"] + 5
+    with torch.no_grad():
+        mdl(**bad)
+    with pytest.raises(IndexError):
+        ops.check_ids()
+
+
+# ------------------------------------------------------------------------------------------------
+# collate functor end to end against the reference's mlm_collate_fn
+# ------------------------------------------------------------------------------------------------
+def test_collate_call_matches_reference(golden_dir, cuda_lib):
+    from a3t_b200.collate import MLMCollateFn
+    from a3t_b200.frontend import LogMelFbank
+
+    fx = torch.load(os.path.join(golden_dir, "collate.pt"), weights_only=False)
+    fe = LogMelFbank(**fx["kw"]).cuda()
+    coll = MLMCollateFn(fe, float_pad_value=0.0, int_pad_value=0, mlm_prob=0.8, mean_phn_span=8, sega_emb=True,
+                        device="cuda")
+    data = fx["data"]
+    variants = {"train": data,
+                "span_boundary": [(u, dict(d, span_boundary=np.array(sb, dtype=np.int64)))
+                                  for (u, d), sb in zip(data, ([3, 9], [0, 15], [10, 20], [5, 5]))],
+                "speech_only": [(u, dict(speech=d["speech"])) for u, d in data]}
+    for name, dd in variants.items():
+        np.random.seed(fx["seeds"][name])
+        ids, out = coll(dd)
+        rid, ref = fx[name]
+        assert ids == rid and set(out) == set(ref), name
+        for k, v in ref.items():
+            got = out[k].cpu()
+            assert got.shape == v.shape, (name, k, got.shape, v.shape)
+            if k == "speech":
+                assert torch.allclose(got, v, atol=1e-4, rtol=1e-4), (name, k)
+            else:  # integer / boolean work: bit-exact
+                assert torch.equal(got.to(v.dtype), v), (name, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# vocoder at the published depth
+# ------------------------------------------------------------------------------------------------
+def test_pwg30_matches_reference(golden_dir, cuda_lib):
+    """30 layers / 3 stacks (dilations up to 512), 200 frames -> 60 000 samples: waveform atol 1e-4."""
+    from a3t_b200.vocoder import ParallelWaveGANGenerator
+
+    f = torch.load(os.path.join(golden_dir, "pwg30.pt"), weights_only=False)
+    gen = ParallelWaveGANGenerator(layers=f["layers"], stacks=f["stacks"], upsample_params={"upsample_scales": f["scales"]})
+    sd = _d384.pwg30_state_dict(f)
+    gen.load_reference_state_dict(sd)
+    gen = gen.cuda()
+    z = _d384.pwg30_z(f)
+    y = gen(f["c"].cuda(), z.cuda())
+    err = float((y.cpu() - f["wav"]).abs().max())
+    assert torch.allclose(y.cpu(), f["wav"], atol=1e-4, rtol=1e-4), err
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM against the CPU oracle on the same bf16-rounded operands (cfg2 shapes, B = 2)
+# ------------------------------------------------------------------------------------------------
+def gb(*shape, seed=0, scale=1.0):
+    """bf16-representable fp32 values (CPU)."""
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(torch.bfloat16).float()
+
+
+def rel_close(a, b, tol):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    sc = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= tol * sc, f"max err {err} vs scale {sc} (tol {tol})"
+
+
+@pytest.fixture(scope="module")
+def tc(cuda_lib):
+    from a3t_b200.backend import CudaBackend
+
+    return CudaBackend("cuda:0", torch.bfloat16, seed=987654321, impl=_lib.IMPL_TC)
+
+
+@pytest.mark.parametrize("taps,C,N,S,B", [
+    (3, 384, 1536, 1152, 2),    # FFN w_1
+    (3, 1536, 384, 1152, 2),    # FFN w_2
+    (1, 384, 1536, 1152, 2),    # qkv4
+    (1, 384, 768, 1152, 2),     # pointwise_conv1
+    (1, 384, 384, 1152, 2),     # linear_out / pointwise_conv2
+    (5, 80, 256, 1024, 2),      # postnet first
+    (5, 256, 256, 1024, 2),     # postnet middle
+    (5, 256, 80, 1024, 2),      # postnet last
+    (1, 80, 384, 1024, 2),      # pre-net
+    (1, 384, 80, 1024, 2),      # mel head
+    (3, 384, 1536, 1692, 1),    # cfg4 sequence length
+])
+def test_tc_conv_family_vs_oracle(tc, taps, C, N, S, B):
+    """fp32 accumulation of identical bf16 products on both sides: fp32 outputs agree to 2e-5 of the output scale
+    (summation order), bf16 outputs to one bf16 ulp (2^-8)."""
+    ob = OracleBackend(seed=987654321)
+    x, w = gb(B, S, C, seed=1), gb(N, C, taps, seed=2, scale=1.0 / math.sqrt(C * taps))
+    bias, res = 0.1 * torch.randn(N, generator=torch.Generator().manual_seed(3)), gb(B, S, N, seed=4)
+    pw_t = tc.pack_weight(w.cuda())
+    pw_o = ob.pack_weight(w)
+    xc = x.cuda().to(torch.bfloat16)
+    for kw in (dict(out_dtype=torch.float32), dict(relu=True, drop=(0.2, 8)), dict(drop=(0.2, 9), residual=True, out_scale=0.5)):
+        kwo, kwc = dict(kw), dict(kw)
+        kwo.pop("out_dtype", None)
+        if kw.get("residual"):
+            kwo["residual"], kwc["residual"] = res, res.cuda()
+        yo = ob.conv_fwd(x, pw_o, bias, **kwo)
+        yc = tc.conv_fwd(xc, pw_t, bias.cuda(), **kwc)
+        rel_close(yc, yo, 2e-5 if yc.dtype == torch.float32 else 4e-3)
+        if "drop" in kw and not kw.get("residual"):
+            assert torch.equal(yc.cpu() == 0, yo == 0)  # bit-identical dropout pattern (ReLU zeros included)
+    dy = gb(B, S, N, seed=5)
+    dyc = dy.cuda().to(torch.bfloat16)
+    mask = (gb(B, S, C, seed=6) > 0).float()
+    rel_close(tc.conv_dgrad(dyc, pw_t, out_dtype=torch.float32), ob.conv_dgrad(dy, pw_o), 2e-5)
+    rel_close(tc.conv_dgrad(dyc, pw_t, mask=mask.cuda().to(torch.bfloat16), mask_scale=1.25, out_dtype=torch.float32),
+              ob.conv_dgrad(dy, pw_o, mask=mask, mask_scale=1.25), 2e-5)
+    rel_close(tc.conv_wgrad(dyc, xc, taps), ob.conv_wgrad(dy, x, taps), 5e-5)   # K = B*S terms, split-K order
+
+
+@pytest.mark.parametrize("B,H,S,dk", [(2, 2, 1152, 192), (1, 2, 1692, 192)])
+def test_tc_attention_contractions_vs_oracle(tc, B, H, S, dk):
+    ob = OracleBackend()
+    D = H * dk
+    qkv4, p = gb(B, S, 4 * D, seed=1, scale=0.5), gb(S, D, seed=2, scale=0.5)
+    qc, pc = qkv4.cuda().to(torch.bfloat16), p.cuda().to(torch.bfloat16)
+    ac_t, bd_t = tc.attn_scores_fwd(qc, pc, H)
+    ac_o, bd_o = ob.attn_scores_fwd(qkv4, p, H)
+    rel_close(ac_t, ac_o, 4e-3)   # bf16 score tensors: one ulp of the largest score
+    rel_close(bd_t, bd_o, 4e-3)
+    Pd = torch.softmax(gb(B, H, S, S, seed=3), -1).to(torch.bfloat16).float()
+    Pdc = tc._scores(B, H, S, "cuda")
+    Pdc.copy_(Pd)
+    rel_close(tc.attn_pv_fwd(Pdc, qc, H), ob.attn_pv_fwd(Pd, qkv4, H), 4e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 variants of the element-wise kernels against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_bf16_layernorm_variants_vs_oracle(tc):
+    ob = OracleBackend(seed=987654321)
+    C, rows = 384, 333
+    g = lambda *s, seed, scale=1.0: torch.randn(*s, generator=torch.Generator().manual_seed(seed)) * scale
+    x, gam, bet = g(2, rows, C, seed=1, scale=2.0), 1 + 0.2 * g(C, seed=2), 0.1 * g(C, seed=3)
+    dy, dres = gb(2, rows, C, seed=4), g(2, rows, C, seed=5)
+    for kw in (dict(), dict(drop=(0.2, 3))):
+        yo, mo, ro = ob.ln_fwd(x, gam, bet, 1e-12, **kw)
+        yc, mc, rc = tc.ln_fwd(x.cuda(), gam.cuda(), bet.cuda(), 1e-12, **kw)
+        assert yc.dtype == torch.bfloat16
+        rel_close(yc, yo, 4e-3)
+        rel_close(mc, mo, 1e-5)
+        rel_close(rc, ro, 1e-4)
+        dxo, dgo, dbo, go, gso = ob.ln_bwd(dy, x, mo, ro, gam, bet, dres=dres, eps=1e-12, nxt=(0.5, (0.2, 11)), **kw)
+        dxc, dgc, dbc, gc, gsc = tc.ln_bwd(dy.cuda().to(torch.bfloat16), x.cuda(), mc, rc, gam.cuda(), bet.cuda(),
+                                          dres=dres.cuda(), eps=1e-12, nxt=(0.5, (0.2, 11)), **kw)
+        assert gc.dtype == torch.bfloat16 and dxc.dtype == torch.float32
+        rel_close(dxc, dxo, 1e-4)
+        rel_close(dgc, dgo, 1e-3)
+        rel_close(dbc, dbo, 1e-3)
+        rel_close(gc, go, 4e-3)
+        assert torch.equal(gc.cpu() == 0, go == 0)
+        rel_close(gsc, gso, 5e-3)   # column sums of the bf16-rounded g
+
+
+@pytest.mark.parametrize("k", [7, 31])
+def test_bf16_glu_dwconv_and_bn_act_vs_oracle(tc, k):
+    ob = OracleBackend(seed=987654321)
+    B, S, C = 2, 515, 384
+    g = lambda *s, seed, scale=1.0: torch.randn(*s, generator=torch.Generator().manual_seed(seed)) * scale
+    u = gb(B, S, 2 * C, seed=1)
+    w, bias = g(C, k, seed=2, scale=0.3), g(C, seed=3, scale=0.1)
+    zo = ob.glu_dwconv_fwd(u, w, bias)
+    zc = tc.glu_dwconv_fwd(u.cuda().to(torch.bfloat16), w.cuda(), bias.cuda())
+    rel_close(zc, zo, 2e-3)   # approx sigmoid in the bf16 mode
+    dz = g(B, S, C, seed=4)
+    duo, dwo, dbo = ob.glu_dwconv_bwd(dz, u, w)
+    duc, dwc, dbc = tc.glu_dwconv_bwd(dz.cuda(), u.cuda().to(torch.bfloat16), w.cuda())
+    assert duc.dtype == torch.bfloat16
+    rel_close(duc, duo, 6e-3)
+    rel_close(dwc.reshape(C, k), dwo.reshape(C, k), 3e-3)
+    rel_close(dbc, dbo, 1e-3)
+    # BatchNorm + activation producing the bf16 GEMM operand
+    rm, rv, nbt = torch.zeros(C), torch.ones(C), torch.zeros((), dtype=torch.long)
+    mo, ro = ob.bn_stats(zo, rm.clone(), rv.clone(), nbt.clone(), 0.1, 1e-5, True)
+    gam, bet = 1 + 0.2 * g(C, seed=5), 0.1 * g(C, seed=6)
+    for act in (1, 2, 0):
+        yo = ob.bn_act_fwd(zo, mo, ro, gam, bet, act, drop=(0.5, 4) if act != 1 else None)
+        yc = tc.bn_act_fwd(zo.cuda(), mo.cuda(), ro.cuda(), gam.cuda(), bet.cuda(), act,
+                           drop=(0.5, 4) if act != 1 else None)
+        assert yc.dtype == torch.bfloat16
+        rel_close(yc, yo, 6e-3)

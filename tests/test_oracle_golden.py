@@ -142,3 +142,96 @@ def test_dropout_pair_hash_independence():
             assert abs(((m - q) * (other - q)).mean()) < 4.0 * q * (1 - q) / np.sqrt(n)
     assert bool(O.keep_mask(17, 0.0, 1, 1).all())
 
+
+
+# ---- round 2: fixtures at the paper width / published vocoder depth / whole collate -----------------
+def test_oracle_graph_matches_reference_at_paper_width(golden_dir):
+    """D=384, H=2, FF=1536, dw 7/31, postnet 5x256, 1+1 blocks, B=2, Ts=1024, Tt=128 ragged: the op graph
+    (a3t_b200/graph.py) over the oracle ops against the numbers the reference produced."""
+    import _d384
+    from a3t_b200 import graph
+    from oracle.fixtures import grad_probe
+    from oracle.oracle_backend import OracleBackend
+
+    fx, b = _d384.load(golden_dir)
+    m = _d384.build(fx)
+    P = {n: p.detach() for n, p in m.named_parameters()}
+    P.update({n: v.clone() for n, v in m.named_buffers()})
+    ops, wc = OracleBackend(), graph.WeightCache()
+    loss, before, after, ctx = graph.forward(ops, P, wc, m.cfg, b, True, True)
+    assert abs(float(loss) - float(fx["loss_train"])) <= 1e-5 * abs(float(fx["loss_train"]))
+    G = graph.backward(ops, P, wc, m.cfg, ctx, torch.ones(1))
+    for n, _ in m.named_parameters():
+        ref = fx["grad_probe"][n]
+        assert float((grad_probe(G[n]) - ref).abs().max()) <= 5e-4 * float(ref.abs().max()) + 5e-5, n
+        assert abs(float(G[n].norm()) - fx["grad_norm"][n]) <= 1e-3 * fx["grad_norm"][n] + 1e-5, n
+    P = {n: p.detach() for n, p in m.named_parameters()}
+    P.update({n: v.clone() for n, v in _d384.build(fx).named_buffers()})
+    le, before, after, _ = graph.forward(ops, P, graph.WeightCache(), m.cfg, b, False, True)
+    assert abs(float(le) - float(fx["loss_eval"])) <= 1e-5 * abs(float(fx["loss_eval"]))
+    assert torch.allclose(before[:, ::8], fx["before_eval"], atol=2e-4, rtol=1e-5)
+    assert torch.allclose(after[:, ::8], fx["after_eval"], atol=2e-4, rtol=1e-5)
+
+
+def test_pwg30_against_reference(golden_dir):
+    """30 layers / 3 stacks / dilations 1..512 / 200 frames (the published generator shape)."""
+    import _d384
+
+    f = torch.load(os.path.join(golden_dir, "pwg30.pt"), weights_only=False)
+    y = O.pwg_generate(f["c"], _d384.pwg30_z(f), _d384.pwg30_state_dict(f), upsample_scales=f["scales"],
+                       layers=f["layers"], stacks=f["stacks"])
+    assert torch.allclose(y, f["wav"], atol=1e-5, rtol=1e-5)
+
+
+def test_oracle_collate_against_reference_mlm_collate_fn(golden_dir):
+    """The oracle's pieces composed as espnet2/train/collate_fn.py:158-287 composes them, on raw utterances,
+    against the reference functor's output dict: text+alignment, span_boundary and speech-only batches."""
+    fx = torch.load(os.path.join(golden_dir, "collate.pt"), weights_only=False)
+    kw = fx["kw"]
+    data = fx["data"]
+
+    def collate(dd, span_boundary=None):
+        B = len(dd)
+        n = max(d["speech"].shape[0] for _, d in dd)
+        wav = torch.zeros(B, n)
+        wl = torch.tensor([d["speech"].shape[0] for _, d in dd])
+        for i, (_, d) in enumerate(dd):
+            wav[i, : wl[i]] = torch.from_numpy(d["speech"])
+        mel, ol = O.stft_logmel(wav, wl, fs=kw["fs"], n_fft=kw["n_fft"], win_length=kw["win_length"], hop=kw["hop_length"],
+                                n_mels=kw["n_mels"], fmin=kw["fmin"], fmax=kw["fmax"])
+        Ts = int(ol.max())
+        mel = mel[:, :Ts]
+        valid = torch.arange(Ts)[None] < ol[:, None]
+        if "text" not in dd[0][1]:
+            m = O.random_spans_noise_mask(Ts, 0.15, min(Ts * 0.15 // 3, 50))
+            mp = torch.from_numpy(m)[None].expand(B, Ts) & valid
+            return dict(speech=mel, text=torch.zeros(B, 1, dtype=torch.long) - 2, masked_position=mp,
+                        speech_segment_pos=torch.zeros(B, Ts, dtype=torch.long),
+                        text_segment_pos=torch.zeros(B, 1, dtype=torch.long))
+        Tt = max(d["text"].shape[0] for _, d in dd)
+        lens = torch.tensor([d["text"].shape[0] for _, d in dd])
+        text = torch.zeros(B, Tt, dtype=torch.long)
+        ts, te = torch.zeros(B, Tt), torch.zeros(B, Tt)
+        for i, (_, d) in enumerate(dd):
+            text[i, : lens[i]] = torch.from_numpy(d["text"])
+            ts[i, : lens[i]] = torch.from_numpy(d["align_start"])
+            te[i, : lens[i]] = torch.from_numpy(d["align_end"])
+        a_s, a_e = O.align_to_frames(ts, kw["fs"], kw["hop_length"]), O.align_to_frames(te, kw["fs"], kw["hop_length"])
+        if span_boundary is not None:
+            mp = O.expand_phone_mask(None, a_s, a_e, lens, valid, span_boundary=span_boundary)
+        else:
+            mp = O.expand_phone_mask(O.draw_phone_masks(lens, 0.8, 8, Tt), a_s, a_e, lens, valid)
+        sp, tp = O.segment_pos(a_s, a_e, lens, Ts, Tt)
+        return dict(speech=mel, text=text, masked_position=mp, speech_segment_pos=sp, text_segment_pos=tp)
+
+    sbs = ([3, 9], [0, 15], [10, 20], [5, 5])
+    for name, dd, sb in (("train", data, None), ("span_boundary", data, sbs),
+                         ("speech_only", [(u, dict(speech=d["speech"])) for u, d in data], None)):
+        np.random.seed(fx["seeds"][name])
+        got = collate(dd, sb)
+        ref = fx[name][1]
+        for k, v in got.items():
+            if k == "speech":
+                assert torch.allclose(v, ref[k], atol=1e-4, rtol=1e-4), (name, k)
+            else:
+                assert torch.equal(v.to(ref[k].dtype), ref[k]), (name, k)
