@@ -14,6 +14,11 @@ import numpy as np
 import torch
 
 from . import _lib
+from .espnet_plugin import espnet_base
+
+# `AbsFeatsExtract` (espnet2/tts/feats_extract/abs_feats_extract.py) when the reference is importable:
+# `feats_extractor_choices` type-checks against it (espnet2/tasks/mlm.py:58-67)
+_FeatsBase = espnet_base("espnet2.tts.feats_extract.abs_feats_extract", "AbsFeatsExtract") or torch.nn.Module
 
 
 def slaney_mel_filterbank(fs: float, n_fft: int, n_mels: int, fmin: float, fmax: float) -> np.ndarray:
@@ -41,7 +46,7 @@ def slaney_mel_filterbank(fs: float, n_fft: int, n_mels: int, fmin: float, fmax:
     return fb.astype(np.float32)
 
 
-class LogMelFbank(torch.nn.Module):
+class LogMelFbank(_FeatsBase):
     def __init__(self, fs: Union[int, str] = 16000, n_fft: int = 1024, win_length: Optional[int] = None,
                  hop_length: int = 256, window: Optional[str] = "hann", center: bool = True,
                  normalized: bool = False, onesided: bool = True, n_mels: int = 80, fmin: Optional[int] = 80,

@@ -22,7 +22,12 @@ import torch
 from torch import nn
 
 from . import graph
+from .espnet_plugin import espnet_base
 from .graph import A3TConfig, WeightCache
+
+# `AbsESPnetModel` (espnet2/train/abs_espnet_model.py:9-42) when the reference is importable: the reference's
+# runtime checks `isinstance(model, AbsESPnetModel)` (abs_task.py:1097-1100, :1794); stand-alone it is nn.Module.
+_ModelBase = espnet_base("espnet2.train.abs_espnet_model", "AbsESPnetModel") or nn.Module
 
 
 class _ParamsOnly(nn.Module):
@@ -219,7 +224,7 @@ class _A3TFunction(torch.autograd.Function):
         return (None, None, None, None) + grads
 
 
-class ESPnetMLMModel(nn.Module):
+class ESPnetMLMModel(_ModelBase):
     """espnet2/tts/sedit/sedit_model.py:47-340 (constructor signature :48-71)."""
 
     def __init__(self, token_list: Union[Tuple[str, ...], List[str]], odim: int, feats_extract, normalize,

@@ -22,12 +22,39 @@ def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "espnet2"))
 
 
+_activated = False
+
+
 def _activate():
+    """Put the reference and the stub packages on sys.path and import the reference's task module once.
+
+    Under pytest the REAL `typeguard` (4.x, loaded by its pytest plugin) is already in sys.modules; ESPnet's
+    `str = None` defaults do not survive it, so the permissive shim is swapped in for the duration
+    of the reference's imports (its modules bind `check_argument_types` at import time) and the real one restored."""
+    global _activated
     if not available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
     for p in (REFERENCE_ROOT, _SHIMS):
         if p not in sys.path:
             sys.path.insert(0, p)
+    if _activated:
+        return
+    import importlib.util
+
+    real = sys.modules.get("typeguard")
+    swapped = real is not None and not getattr(real, "_A3T_SHIM", False)
+    if swapped:
+        spec = importlib.util.spec_from_file_location("typeguard", os.path.join(_SHIMS, "typeguard", "__init__.py"))
+        shim = importlib.util.module_from_spec(spec)
+        sys.modules["typeguard"] = shim
+        spec.loader.exec_module(shim)
+    try:
+        import espnet2.tasks.mlm  # noqa: F401  (pulls in every reference module the path uses)
+        import espnet2.gan_tts.parallel_wavegan  # noqa: F401
+    finally:
+        if swapped:
+            sys.modules["typeguard"] = real
+    _activated = True
 
 
 PAPER_YAML = "egs2/vctk/sedit/conf/fsp2_conformer.yaml"

@@ -1,4 +1,5 @@
 """Permissive typeguard shim (typeguard 4.x rejects ESPnet's `str = None` defaults)."""
+_A3T_SHIM = True
 def check_argument_types(*a, **k):
     return True
 def check_return_type(*a, **k):

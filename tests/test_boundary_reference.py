@@ -1,0 +1,139 @@
+"""The drop-in boundary exercised through the REFERENCE's own task code (build container only: needs
+/root/reference; the GPU box skips the construction part and runs the GPU part against the fixture).
+
+`a3t_b200.espnet_plugin.register()` patches `espnet2.tasks.mlm`; then the reference's unmodified
+`MLMTask.build_model(args)` with `egs2/vctk/sedit/conf/fsp2_conformer.yaml` (mlm.py:329-443) must return the B200
+model, pass the `isinstance(model, AbsESPnetModel)` check of `abs_task.py:1097-1100`, be initialised by the
+reference's `initialize()` and accept the reference model's `state_dict`; `build_model_from_file` must apply its
+`encoder.embed -> encoder.speech_embed` key rename (mlm.py:490-493) on the way in."""
+import argparse
+import os
+
+import pytest
+import torch
+
+from oracle import ref_harness as R
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="reference tree not present (GPU box)")
+
+
+def _args(conf, vocab=73):
+    return argparse.Namespace(
+        token_list=["<blank>", "<unk>"] + [f"p{i}" for i in range(vocab - 3)] + ["<sos/eos>"], odim=80, input_size=80,
+        feats_extract="fbank", feats_extract_conf={}, normalize=None, normalize_conf={}, use_scaled_pos_enc=False,
+        encoder="conformer", encoder_conf=dict(conf["encoder_conf"]), decoder="conformer",
+        decoder_conf=dict(conf["decoder_conf"]), model_conf=dict(conf["model_conf"]), init="xavier_uniform")
+
+
+@pytest.fixture()
+def patched():
+    """register() mutates the reference's module: restore it afterwards so other tests see the stock reference."""
+    R._activate()
+    import espnet2.tasks.mlm as mlm
+
+    saved = (dict(mlm.encoder_choices.classes), dict(mlm.decoder_choices.classes),
+             dict(mlm.feats_extractor_choices.classes), mlm.ESPnetMLMModel, mlm.ESPnetMLMEncAsDecoderModel,
+             mlm.ESPnetMLMTTSModel, mlm.MLMCollateFn)
+    import a3t_b200.espnet_plugin as plug
+
+    task = plug.register()
+    yield task, mlm
+    mlm.encoder_choices.classes.clear(); mlm.encoder_choices.classes.update(saved[0])
+    mlm.decoder_choices.classes.clear(); mlm.decoder_choices.classes.update(saved[1])
+    mlm.feats_extractor_choices.classes.clear(); mlm.feats_extractor_choices.classes.update(saved[2])
+    (mlm.ESPnetMLMModel, mlm.ESPnetMLMEncAsDecoderModel, mlm.ESPnetMLMTTSModel, mlm.MLMCollateFn) = saved[3:]
+
+
+@needs_ref
+def test_build_model_through_reference_task(patched):
+    task, mlm = patched
+    import a3t_b200.model as M
+    from espnet2.train.abs_espnet_model import AbsESPnetModel
+    from espnet2.tts.feats_extract.abs_feats_extract import AbsFeatsExtract
+    from a3t_b200.frontend import LogMelFbank
+
+    conf = R.model_conf("paper")                         # conf/fsp2_conformer.yaml as shipped
+    torch.manual_seed(0)
+    model = task.build_model(_args(conf))
+    assert type(model) is M.ESPnetMLMEncAsDecoderModel
+    assert isinstance(model, AbsESPnetModel)             # abs_task.py:1097-1100
+    assert isinstance(model, mlm.ESPnetMLMModel)         # mlm.py:476-479 (build_model_from_file)
+    assert isinstance(model.encoder, M.MLMEncoder) and isinstance(model.decoder, M.MLMDecoder)
+    assert issubclass(LogMelFbank, AbsFeatsExtract)      # mlm.py:58-67 type_check
+    assert len(model.state_dict()) == 363                # SURVEY 8b checkpoint layout
+    # initialize(model, "xavier_uniform") ran on the B200 module tree: 1-D params zero except Embedding / LayerNorm
+    assert float(model.sfc.bias.abs().sum()) == 0.0
+    assert float(model.encoder.encoders[0].conv_module.norm.weight.abs().sum()) == 0.0   # BatchNorm gamma zeroed
+    assert float(model.encoder.after_norm.weight.min()) == 1.0
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params == 67_691_872 or n_params > 60_000_000, n_params
+    # abs_task.py:1101: model.to(dtype=float32, device=...) must work on the module tree
+    model = model.to(dtype=torch.float32, device="cpu")
+    assert model.collect_feats(torch.zeros(1, 10, 80), torch.tensor([10]), None, None)["feats"].shape == (1, 10, 80)
+
+
+@needs_ref
+def test_state_dict_is_interchangeable_with_stock_reference(golden_dir):
+    """Stock reference model (no patch) -> state_dict -> B200 model built with the same conf: strict load."""
+    import a3t_b200.model as M
+
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+    ref = R.build_reference_model(fx["conf"], vocab=fx["vocab"])
+    conf = fx["conf"]
+    m = M.build_model(conf["encoder_conf"], conf["decoder_conf"], conf["model_conf"], vocab_size=fx["vocab"])
+    missing, unexpected = m.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing and not unexpected
+    back = ref.load_state_dict(m.state_dict(), strict=True)
+    assert not back.missing_keys and not back.unexpected_keys
+
+
+@needs_ref
+def test_build_model_from_file_renames_legacy_keys(patched, tmp_path, golden_dir):
+    """mlm.py:455-496: config.yaml + checkpoint whose pre-net keys still carry the old `encoder.embed.*` names."""
+    import yaml
+
+    task, mlm = patched
+    import a3t_b200.model as M
+
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+    a = _args(fx["conf"], vocab=fx["vocab"])
+    cfg = dict(vars(a))
+    cfg["model_conf"] = dict(cfg["model_conf"], ctc_weight=0.0)   # popped by build_model_from_file (mlm.py:471-472)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(cfg))
+    legacy = {k.replace("encoder.speech_embed", "encoder.embed"): v for k, v in fx["state_dict"].items()}
+    assert any(k.startswith("encoder.embed") for k in legacy)
+    torch.save(legacy, tmp_path / "model.pth")
+    model, args = task.build_model_from_file(tmp_path / "config.yaml", tmp_path / "model.pth", device="cpu")
+    assert type(model) is M.ESPnetMLMEncAsDecoderModel
+    sd = model.state_dict()
+    for k, v in fx["state_dict"].items():
+        assert torch.equal(sd[k], v), k
+
+
+@pytest.mark.gpu
+def test_reference_built_model_runs_model_call_on_gpu(golden_dir, cuda_lib):
+    """`model(**batch)` exactly as `Trainer.train_one_epoch` calls it (trainer.py:545), on the GPU; when the
+    reference tree is present the model comes out of the reference's own `MLMTask.build_model`."""
+    fx = torch.load(os.path.join(golden_dir, "model_tiny.pt"), weights_only=False)
+    conf = fx["conf"]
+    if R.available():
+        R._activate()
+        import a3t_b200.espnet_plugin as plug
+
+        task = plug.register()
+        model = task.build_model(_args(conf, vocab=fx["vocab"]))
+    else:
+        from a3t_b200.model import build_model
+
+        model = build_model(conf["encoder_conf"], conf["decoder_conf"], conf["model_conf"], vocab_size=fx["vocab"])
+    for mod in (model.encoder, model.decoder):
+        mod.dropout_rate = mod.positional_dropout_rate = mod.attention_dropout_rate = 0.0
+    model.postnet.dropout_rate = 0.0
+    model.load_state_dict(fx["state_dict"])
+    model = model.to(dtype=torch.float32, device="cuda").train()
+    batch = {k: v.cuda() for k, v in fx["batch"].items()}
+    loss, stats, weight = model(**batch)
+    loss.backward()
+    assert abs(float(loss) - float(fx["loss_train"])) <= 2e-4 * abs(float(fx["loss_train"]))
+    g = model.sfc.weight.grad.cpu()
+    assert float((g - fx["grads"]["sfc.weight"]).abs().max()) <= 5e-4 * float(fx["grads"]["sfc.weight"].abs().max()) + 5e-5
