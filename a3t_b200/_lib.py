@@ -77,6 +77,9 @@ _SIGS = {
     "a3t_embed_assemble_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _F, _P, _U, _U, _I, _I, _P],
     "a3t_relpos_softmax_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_relpos_softmax_bwd": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_attn_fused_supported": [_I, _I, _I, _I],
+    "a3t_relpos_attn_fwd": [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_relpos_attn_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_glu_dwconv_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "a3t_dwconv_bwd_blocks": [_I, _I],
     "a3t_glu_dwconv_bwd": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -98,7 +101,7 @@ _SIGS = {
 }
 # entry points that return a count / flag rather than a status code
 _PLAIN_INT = {"a3t_version", "a3t_layernorm_bwd_blocks", "a3t_colsum_blocks", "a3t_dwconv_bwd_blocks",
-              "a3t_gemm_tc_supported", "a3t_gemm_fallback_count"}
+              "a3t_gemm_tc_supported", "a3t_gemm_fallback_count", "a3t_attn_fused_supported"}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["a3t_last_error"])
 

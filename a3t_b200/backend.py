@@ -491,6 +491,67 @@ class CudaBackend:
             return tmp.view(S, D)
         return self.colsum(tmp.view(Bn, S * D)).view(S, D)
 
+    # ------------------------------------------------------------------ fused attention (bf16 / tcgen05)
+    def attn_fused_ok(self, Bn, H, S, D) -> bool:
+        """True when the fused tcgen05 attention kernels take this shape (bf16 mode, head width 64 / 128 / 192)."""
+        return (self.act_dtype == torch.bfloat16 and self.impl != _lib.IMPL_SIMT
+                and call("a3t_attn_fused_supported", Bn, H, S, D) == 1)
+
+    def attn_fwd_fused(self, qkv4, p, keymask, H, scale, *, drop=None):
+        """ctx = attention(qkv4, p) with the scores kept on chip.  Returns (ctx (B,S,D), bd_raw, lse): bd_raw =
+        (q+v) p^T is the one (B,H,S,S) tensor still materialised (bf16, by the batched GEMM); both it and lse are
+        what the fused backward recomputes the probabilities from."""
+        Bn, S, D4 = qkv4.shape
+        D = D4 // 4
+        dk = D // H
+        bd = self._scores(Bn, H, S, qkv4.device)
+        ld, sb1, sb2 = self._sstr(bd)
+        dt = _dt(qkv4)
+        d = self._desc(S, S, dk, batch1=Bn, batch2=H, dtype_a=dt, dtype_b=dt, dtype_c=_dt(bd), sa_m=D4, sa_k=1,
+                       sa_b1=S * D4, sa_b2=dk, sc_m=ld, sc_n=1, sc_b1=sb1, sc_b2=sb2, sb_n=p.stride(0), sb_k=1, sb_b1=0,
+                       sb_b2=dk)
+        self._gemm(d, qkv4, p, bd, a_off=D)
+        ctx = torch.empty(Bn, S, D, dtype=torch.bfloat16, device=qkv4.device)
+        lse = torch.empty(Bn, H, S, dtype=torch.float32, device=qkv4.device)
+        pr, seed, site = self._drop(drop)
+        call("a3t_relpos_attn_fwd", _p(qkv4), _p(bd), ld, _p(_u8(keymask)), _p(ctx), _p(lse), Bn, H, S, D, scale, pr, seed,
+             site, _stream(qkv4))
+        return ctx, bd, lse
+
+    def attn_bwd_fused(self, dctx, ctx, lse, bd, qkv4, p, keymask, H, scale, dqkv4, *, drop=None):
+        """Backward of attn_fwd_fused: fills dqkv4 = [d(q+u) | d(q+v) | dk | dv] and returns dp (S,D) fp32."""
+        Bn, S, D4 = qkv4.shape
+        D = D4 // 4
+        dk = D // H
+        dev = qkv4.device
+        pd, ds, dbd = self._like(bd), self._like(bd), self._like(bd)
+        ld, sb1, sb2 = self._sstr(bd)
+        pr, seed, site = self._drop(drop)
+        call("a3t_relpos_attn_bwd", _p(qkv4), _p(bd), ld, _p(_u8(keymask)), _p(ctx), _p(dctx), _p(lse), _p(dqkv4), _p(pd),
+             _p(ds), _p(dbd), Bn, H, S, D, scale, pr, seed, site, _stream(qkv4))
+        dts, dtq = _dt(ds), _dt(qkv4)
+        a_row = dict(sa_m=ld, sa_k=1, sa_b1=sb1, sa_b2=sb2)   # A[i, j]
+        a_col = dict(sa_m=1, sa_k=ld, sa_b1=sb1, sa_b2=sb2)   # A^T
+        c_qkv = dict(sc_m=D4, sc_n=1, sc_b1=S * D4, sc_b2=dk)
+        b_qkv = dict(sb_n=1, sb_k=D4, sb_b1=S * D4, sb_b2=dk)
+        base = dict(batch1=Bn, batch2=H, dtype_a=dts, dtype_b=dtq, dtype_c=_dt(dqkv4))
+        # dv = Pd^T dctx
+        d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=dts, dtype_b=_dt(dctx), dtype_c=_dt(dqkv4), **a_col, sb_n=1,
+                       sb_k=D, sb_b1=S * D, sb_b2=dk, **c_qkv)
+        self._gemm(d, pd, dctx, dqkv4, c_off=3 * D)
+        # dk = dS^T (q+u);  d(q+v) = dBD_raw p;  dp = sum_b dBD_raw^T (q+v)
+        self._gemm(self._desc(S, dk, S, **base, **a_col, **b_qkv, **c_qkv), ds, qkv4, dqkv4, b_off=0, c_off=2 * D)
+        d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=dts, dtype_b=_dt(p), dtype_c=_dt(dqkv4), **a_row, sb_n=1,
+                       sb_k=p.stride(0), sb_b1=0, sb_b2=dk, **c_qkv)
+        self._gemm(d, dbd, p, dqkv4, c_off=D)
+        tmp = torch.empty(Bn, S, D, dtype=torch.float32, device=dev)
+        d = self._desc(S, dk, S, batch1=Bn, batch2=H, dtype_a=dts, dtype_b=dtq, dtype_c=A3T_F32, **a_col, **b_qkv, sc_m=D,
+                       sc_n=1, sc_b1=S * D, sc_b2=dk)
+        self._gemm(d, dbd, qkv4, tmp, b_off=D)
+        if Bn == 1:
+            return tmp.view(S, D)
+        return self.colsum(tmp.view(Bn, S * D)).view(S, D)
+
     # ------------------------------------------------------------------ conv module
     def glu_dwconv_fwd(self, u, w, bias):
         Bn, S, C2 = u.shape

@@ -1,0 +1,787 @@
+// Fused legacy relative-position attention for sm_100a (tcgen05 / TMEM / TMA): the score tensors AC, P and dP of
+// transformer/attention.py:167-209 never reach HBM.
+//
+//   forward  (attn_fwd_kernel):  one CTA per (utterance, head, 128-query tile), loop over 128-key tiles:
+//       S = (q+u) K^T on the tensor cores into TMEM (double buffered)  ->  + rel_shift(BD_raw) read with its skew
+//       -> key-pad mask, online softmax (lazy rescale), dropout hash  ->  P (bf16) to shared memory  ->
+//       O += P V on the tensor cores (accumulator resident in TMEM)  ->  ctx = O / l, lse.
+//   backward (attn_bwd_kernel):  same decomposition, 64-key tiles: recompute S and P from lse, dP = dO V^T,
+//       dS = P * (dropout'(dP) - delta) * scale;  dQu += dS K on the tensor cores (TMEM resident);  the three
+//       operands the remaining batched contractions need are written once each: P_dropped (for dV = Pd^T dO),
+//       dS (for dK = dS^T (q+u)) and dBD_raw = rel_shift^T(dS) (for d(q+v) = dBD_raw p, dp = dBD_raw^T (q+v)).
+//
+// BD_raw = (q+v) p^T is produced by the batched GEMM (gemm_tc.cu) in bf16 and consumed here through
+// rel_shift's index map (attention.py:145-165): BD[i,j] = BD_raw[i, S-1-i+j] (j <= i), 0 (j = i+1),
+// BD_raw[i+1, j-i-2] (j >= i+2).  Rows shift by one element per query, so the tile is loaded with lanes along
+// the key axis (coalesced 2-byte loads, any alignment) and transposed to the thread-per-query layout of
+// tcgen05.ld through a small per-warp shared-memory buffer; the backward scatters dBD_raw the same way.
+//
+// Replaces: attention.py:190-209 (matmul / rel_shift / softmax / dropout / matmul) and its autograd backward.
+#include <float.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace a3t {
+namespace fa {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int NUM_SM_WARPS = 8;                       // softmax warps: (warp & 3) = TMEM lane quarter, (warp >> 2) = column half
+constexpr int PRODUCER_WARP = 8, MMA_WARP = 9;
+constexpr int NUM_THREADS = 32 * (NUM_SM_WARPS + 2);
+constexpr int SMEM_MAX = 227 * 1024;
+
+struct Params {
+  const __nv_bfloat16* bd_raw;  // (B,H,S,ld) bf16
+  const uint8_t* keymask;       // (B,S), 1 = valid key
+  const unsigned long long* seed;
+  float* lse;                   // (B,H,S) log2-domain log-sum-exp of the scaled scores
+  __nv_bfloat16* ctx;           // fwd out / bwd in: (B,S,D)
+  const __nv_bfloat16* dctx;    // bwd in: (B,S,D)
+  __nv_bfloat16* dq;            // bwd out: dqkv4 base (B,S,4D); d(q+u) goes to columns [h*dk, (h+1)*dk)
+  __nv_bfloat16* pd;            // bwd out: (B,H,S,ld) dropped probabilities
+  __nv_bfloat16* dbd;           // bwd out: (B,H,S,ld) dBD_raw
+  int64_t ld;                   // row pitch of every (B,H,S,S) tensor, elements
+  int B, H, S, D;
+  float scale, c2;              // 1/sqrt(dk); scale * log2(e)
+  float drop_p;
+  uint32_t site;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// rel_shift source of key j for query i inside one (b,h) block of BD_raw (pitch ld); -1: the structural zero / outside
+__device__ __forceinline__ int64_t shift_src(int i, int j, int S, int64_t ld) {
+  if (i >= S || j >= S || j == i + 1) return -1;
+  return j <= i ? (int64_t)i * ld + (S - 1 - i) + j : (int64_t)(i + 1) * ld - (i + 2) + j;
+}
+
+// Bias sub-tile (ROWS queries x COLS keys) of this warp: coalesced loads (lane = key), transposition through tbuf
+// (pitch COLS*2+16 bytes), thread = query read-back of COLS bf16 packed in COLS/2 words.  Rows: i_first .. +ROWS-1
+// are stored at buffer rows 0..ROWS-1; the caller's lane reads buffer row `myrow` (< ROWS) if `mine`.
+template <int COLS, int ROWS>
+__device__ __forceinline__ void load_bias_tile(const __nv_bfloat16* __restrict__ G, int i_first, int j_first, int S, int64_t ld,
+                                               uint32_t tbuf, int lane, int myrow, bool mine, uint32_t (&out)[COLS / 2]) {
+  constexpr int PITCH = COLS * 2 + 16;
+  constexpr int PER = COLS / 32;  // keys per lane per row
+  const unsigned short* Gs = reinterpret_cast<const unsigned short*>(G);
+#pragma unroll 1
+  for (int r0 = 0; r0 < ROWS; r0 += 8) {
+    unsigned short v[8][PER];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int i = i_first + r0 + r;
+#pragma unroll
+      for (int e = 0; e < PER; e++) {
+        const int64_t src = shift_src(i, j_first + lane + 32 * e, S, ld);
+        v[r][e] = src >= 0 ? __ldg(Gs + src) : (unsigned short)0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int e = 0; e < PER; e++)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(tbuf + (r0 + r) * PITCH + 2 * (lane + 32 * e)), "h"(v[r][e]) : "memory");
+  }
+  __syncwarp();
+  if (mine) {
+#pragma unroll
+    for (int c = 0; c < COLS / 8; c++)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(out[4 * c]), "=r"(out[4 * c + 1]), "=r"(out[4 * c + 2]), "=r"(out[4 * c + 3])
+                   : "r"(tbuf + myrow * PITCH + 16 * c)
+                   : "memory");
+  }
+  __syncwarp();
+}
+
+// validity bits of COLS keys starting at j_first (bit c = key j_first + c is a real, non-padded key)
+template <int COLS>
+__device__ __forceinline__ void key_bits(const uint8_t* __restrict__ km, int j_first, int S, int lane, uint32_t (&bits)[COLS / 32]) {
+#pragma unroll
+  for (int e = 0; e < COLS / 32; e++) {
+    const int j = j_first + 32 * e + lane;
+    const bool ok = j < S && km[j] != 0;
+    bits[e] = __ballot_sync(0xffffffffu, ok);
+  }
+}
+
+// keep flags of COLS consecutive elements starting at element index idx0: word k holds the 16-bit random values of
+// elements 2k (low half) and 2k+1 (high half) -- the pair hash of common.cuh re-aligned to an odd start
+template <int COLS>
+__device__ __forceinline__ void drop_words(const Drop& dr, unsigned long long idx0, uint32_t (&w)[COLS / 2]) {
+  const uint32_t f0 = drop_fold(idx0);
+  const uint32_t pbase = f0 >> 1;
+  const uint32_t sh = (f0 & 1u) * 16u;
+  uint32_t hprev = drop_hash(dr, pbase);
+#pragma unroll
+  for (int k = 0; k < COLS / 2; k++) {
+    const uint32_t hnext = drop_hash(dr, pbase + k + 1);
+    w[k] = __funnelshift_r(hprev, hnext, sh);
+    hprev = hnext;
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int DK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ Params p) {
+  A3T_PDL_TRIGGER();
+  constexpr int NC = DK / 64;                  // 64-wide chunks of the head dimension
+  constexpr uint32_t QB = NC * 16384u;         // one 128 x DK bf16 operand tile
+  constexpr int T_BYTES = 32 * 144;
+  constexpr int HALF = DK / 2;                 // O columns per thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = sQ + QB, sV = sK + QB, sP = sV + QB, sT = sP + 32768u, sRed = sT + NUM_SM_WARPS * T_BYTES,
+                 sBar = sRed + 2048u;
+  const uint32_t q_full = sBar, k_full = sBar + 8, k_empty = sBar + 16, v_full = sBar + 24, v_empty = sBar + 32,
+                 p_full = sBar + 72, p_empty = sBar + 80, o_full = sBar + 88, tmem_slot = sBar + 96;
+  auto s_full = [&](int i) { return sBar + 40u + 8u * i; };
+  auto s_empty = [&](int i) { return sBar + 56u + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, H = p.H, D = p.D;
+  const int nqt = (S + BM - 1) / BM, nkt = nqt;
+  const int qt = blockIdx.x % nqt, bh = blockIdx.x / nqt;
+  const int h = bh % H, b = bh / H;
+  const int i0 = qt * BM;
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(s_empty(0), NUM_SM_WARPS); mbar_init(s_empty(1), NUM_SM_WARPS);
+    mbar_init(p_full, NUM_SM_WARPS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  A3T_PDL_WAIT();
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      // operand tiles are stored as 8 KB boxes of 64 rows x 64 columns (128-byte swizzled rows)
+      mbar_expect_tx(q_full, QB);
+      for (int c = 0; c < NC; c++)
+        for (int r = 0; r < 2; r++) tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
+      for (int t = 0; t < nkt; t++) {
+        const int j0 = t * 128;
+        if (t > 0) mbar_wait(k_empty, (t - 1) & 1);
+        mbar_expect_tx(k_full, QB);
+        for (int c = 0; c < NC; c++)
+          for (int r = 0; r < 2; r++)
+            tma_load_4d(sK + c * 16384 + r * 8192, &tmQKV, k_full, 2 * D + h * DK + 64 * c, j0 + 64 * r, b, 0);
+        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
+        mbar_expect_tx(v_full, QB);
+        for (int kc = 0; kc < 2; kc++)   // V as the MN-major B operand of P V: per 64-key chunk, NC atoms of 64 head columns
+          for (int a = 0; a < NC; a++)
+            tma_load_4d(sV + kc * (NC * 8192) + a * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * a, j0 + 64 * kc, b, 0);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+      const uint64_t dQ = make_smem_desc(sQ, 16), dK = make_smem_desc(sK, 16), dP = make_smem_desc(sP, 16);
+      const uint64_t dV = make_smem_desc(sV, 8192);
+      auto issue_s = [&](int t) {
+        mbar_wait(k_full, t & 1);
+        if (t >= 2) mbar_wait(s_empty(t & 1), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + 128u * (t & 1);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(d, dQ + (uint64_t)((c * 16384 + k * 32) >> 4), dK + (uint64_t)((c * 16384 + k * 32) >> 4), idesc_s,
+                      (c | k) ? 1u : 0u);
+        umma_commit(k_empty);
+        umma_commit(s_full(t & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int t = 0; t < nkt; t++) {
+        if (t + 1 < nkt) issue_s(t + 1);
+        mbar_wait(p_full, t & 1);
+        mbar_wait(v_full, t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_O, dP + (uint64_t)((kc * 16384 + k * 32) >> 4), dV + (uint64_t)((kc * (NC * 8192) + k * 2048) >> 4),
+                      idesc_o, (t | kc | k) ? 1u : 0u);
+        umma_commit(v_empty);
+        umma_commit(p_empty);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================================== softmax warps ====================================
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane, i = i0 + row;
+    const uint32_t tbuf = sT + warp * T_BYTES;
+    const __nv_bfloat16* G = p.bd_raw + (int64_t)bh * S * p.ld;
+    const uint8_t* km = p.keymask + (int64_t)b * S;
+    const Drop dr = make_drop(p.drop_p, p.seed, p.site);
+    const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
+    const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    const float c2 = p.c2;
+    for (int t = 0; t < nkt; t++) {
+      const int j0 = t * 128 + 64 * hh;
+      uint32_t bw[32], kb[2];
+      load_bias_tile<64, 32>(G, i0 + q * 32, j0, S, p.ld, tbuf, lane, lane, true, bw);
+      key_bits<64>(km, j0, S, lane, kb);
+      mbar_wait(s_full(t & 1), (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      {
+        const uint32_t ta = tmem_base + 128u * (t & 1) + lane_t + 64u * hh;
+        tmem_ld32(ta, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(t & 1));
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c++) {
+        const float bias = (c & 1) ? bf_hi(bw[c >> 1]) : bf_lo(bw[c >> 1]);
+        float x = (__uint_as_float(s[c]) + bias) * c2;
+        x = ((kb[c >> 5] >> (c & 31)) & 1u) ? x : -INFINITY;
+        s[c] = __float_as_uint(x);
+        mx = fmaxf(mx, x);
+      }
+      // the two threads of a row (this warp and warp ^ 4) agree on the tile maximum
+      const uint32_t red = sRed + (uint32_t)(t & 1) * 1024u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (hh * 128 + row) * 4), "f"(mx) : "memory");
+      named_bar(1 + q, 64);
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(red + ((hh ^ 1) * 128 + row) * 4) : "memory");
+      const float m_new = fmaxf(m, fmaxf(mx, other));
+      // lazy rescale: the running maximum only moves when it grows by more than 2^8 (P stays <= 256: exact enough in
+      // bf16 / fp32 and the accumulator in TMEM is rarely touched)
+      const bool resc = m_new > m + 8.f;
+      float fac = 1.f;
+      if (resc) {
+        fac = ex2(m - m_new);   // m = -inf on the first tile: 0
+        l *= fac;
+        m = m_new;
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      uint32_t rw[32];
+      if (dr.on) drop_words<64>(dr, drow + (unsigned long long)j0, rw);
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        float p0 = ex2(__uint_as_float(s[2 * k]) - m_use), p1 = ex2(__uint_as_float(s[2 * k + 1]) - m_use);
+        l += p0 + p1;
+        if (dr.on) {
+          p0 = ((rw[k] & 0xFFFFu) >= dr.thr) ? p0 * dr.inv_keep : 0.f;
+          p1 = ((rw[k] >> 16) >= dr.thr) ? p1 * dr.inv_keep : 0.f;
+        }
+        pk[k] = pack_bf16(p0, p1);
+      }
+      if (t > 0) {
+        mbar_wait(p_empty, (t - 1) & 1);   // P V of the previous tile has read the P buffer and updated O
+        if (__any_sync(0xffffffffu, resc)) {
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < HALF / 32; g++) {
+            uint32_t o[32];
+            const uint32_t ta = tmem_O + lane_t + (uint32_t)(hh * HALF + g * 32);
+            tmem_ld32(ta, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; c++) o[c] = __float_as_uint(__uint_as_float(o[c]) * fac);
+            tmem_st32(ta, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      const uint32_t prow = sP + hh * 16384 + row * 128;
+      const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((u ^ sw) << 4)), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                     "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                     : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: ctx = O / l, lse ----
+    const uint32_t red = sRed + (uint32_t)(nkt & 1) * 1024u;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (hh * 128 + row) * 4), "f"(l) : "memory");
+    named_bar(1 + q, 64);
+    float lo;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(red + ((hh ^ 1) * 128 + row) * 4) : "memory");
+    const float ltot = l + lo;
+    const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* crow = p.ctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF;
+#pragma unroll
+    for (int g = 0; g < HALF / 32; g++) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_t + (uint32_t)(hh * HALF + g * 32), o);
+      tmem_ld_wait();
+      if (i < S) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * u]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+          *reinterpret_cast<uint4*>(crow + g * 32 + 8 * u) = v;
+        }
+      }
+    }
+    if (hh == 0 && i < S) p.lse[(int64_t)bh * S + i] = ltot > 0.f ? m + log2f(ltot) : 1e30f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// 64-key tiles.  Shared memory: Qu and dO resident (2 x 128 x DK), K and V double buffered (2 x 2 x 64 x DK), the dS
+// operand tile (128 x 64), per-warp transposition buffers.  TMEM: S and dP double buffered (4 x 64 columns), dQu (DK).
+template <int DK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ Params p) {
+  A3T_PDL_TRIGGER();
+  constexpr int NC = DK / 64;
+  constexpr uint32_t QB = NC * 16384u;         // 128 x DK
+  constexpr uint32_t KB = NC * 8192u;          // 64 x DK
+  constexpr int T_BYTES = 16 * 80;             // 16 rows x (32 keys * 2 B + 16)
+  constexpr int HALF = DK / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sDO = sQ + QB, sK = sDO + QB, sV = sK + 2 * KB, sDS = sV + 2 * KB, sT = sDS + 16384u,
+                 sRed = sT + NUM_SM_WARPS * T_BYTES, sBar = sRed + 1024u;
+  const uint32_t q_full = sBar, ds_full = sBar + 8, ds_empty = sBar + 16, o_full = sBar + 24, tmem_slot = sBar + 32;
+  auto kv_full = [&](int i) { return sBar + 40u + 8u * i; };
+  auto kv_empty = [&](int i) { return sBar + 56u + 8u * i; };
+  auto s_full = [&](int i) { return sBar + 72u + 8u * i; };
+  auto s_empty = [&](int i) { return sBar + 88u + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, H = p.H, D = p.D;
+  const int nqt = (S + BM - 1) / BM, nkt = (S + 63) / 64;
+  const int qt = blockIdx.x % nqt, bh = blockIdx.x / nqt;
+  const int h = bh % H, b = bh / H;
+  const int i0 = qt * BM;
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDS) : "memory");
+    mbar_init(q_full, 1); mbar_init(ds_full, NUM_SM_WARPS); mbar_init(ds_empty, 1); mbar_init(o_full, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(kv_full(i), 1); mbar_init(kv_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(s_empty(i), NUM_SM_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  A3T_PDL_WAIT();
+  // TMEM columns: S buffers at 0 / 64, dP buffers at 128 / 192, dQu at 256
+  const uint32_t tmem_dQ = tmem_base + 256;
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * QB);
+      for (int c = 0; c < NC; c++)
+        for (int r = 0; r < 2; r++) {
+          tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
+          tma_load_4d(sDO + c * 16384 + r * 8192, &tmDO, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
+        }
+      for (int t = 0; t < nkt; t++) {
+        const int st = t & 1, j0 = t * 64;
+        if (t >= 2) mbar_wait(kv_empty(st), ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full(st), 2 * KB);
+        for (int c = 0; c < NC; c++) {
+          tma_load_4d(sK + st * KB + c * 8192, &tmQKV, kv_full(st), 2 * D + h * DK + 64 * c, j0, b, 0);
+          tma_load_4d(sV + st * KB + c * 8192, &tmQKV, kv_full(st), 3 * D + h * DK + 64 * c, j0, b, 0);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+      const uint64_t dQ = make_smem_desc(sQ, 16), dDO = make_smem_desc(sDO, 16), dDS = make_smem_desc(sDS, 16);
+      auto issue_s = [&](int t) {
+        const int st = t & 1;
+        mbar_wait(kv_full(st), (t >> 1) & 1);
+        if (t >= 2) mbar_wait(s_empty(st), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dK = make_smem_desc(sK + st * KB, 16), dV = make_smem_desc(sV + st * KB, 16);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + 64u * st, dQ + (uint64_t)((c * 16384 + k * 32) >> 4), dK + (uint64_t)((c * 8192 + k * 32) >> 4),
+                      idesc_s, (c | k) ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + 128u + 64u * st, dDO + (uint64_t)((c * 16384 + k * 32) >> 4),
+                      dV + (uint64_t)((c * 8192 + k * 32) >> 4), idesc_s, (c | k) ? 1u : 0u);
+        umma_commit(s_full(st));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int t = 0; t < nkt; t++) {
+        if (t + 1 < nkt) issue_s(t + 1);
+        mbar_wait(ds_full, t & 1);
+        tc_fence_after();
+        // dQu += dS (128 x 64 keys, K-major) * K (64 keys x DK: the K tile read MN-major, NC atoms 8 KB apart)
+        const uint64_t dKm = make_smem_desc(sK + (t & 1) * KB, 8192);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_dQ, dDS + (uint64_t)((k * 32) >> 4), dKm + (uint64_t)((k * 2048) >> 4), idesc_q, (t | k) ? 1u : 0u);
+        // the same shared-memory tile goes to HBM as dS (for dK = dS^T (q+u)); its reads must finish before reuse
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)&tmDS),
+                     "r"(sDS), "r"(t * 64), "r"(i0), "r"(h), "r"(b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        umma_commit(kv_empty(t & 1));
+        umma_commit(ds_empty);
+      }
+      umma_commit(o_full);
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane, i = i0 + row;
+    const bool row_ok = i < S;
+    const uint32_t tbuf = sT + warp * T_BYTES;
+    const int64_t blk = (int64_t)bh * S * p.ld;
+    const __nv_bfloat16* G = p.bd_raw + blk;
+    unsigned short* const dbd = reinterpret_cast<unsigned short*>(p.dbd + blk);
+    unsigned short* const pdo = reinterpret_cast<unsigned short*>(p.pd + blk);
+    const uint8_t* km = p.keymask + (int64_t)b * S;
+    const Drop dr = make_drop(p.drop_p, p.seed, p.site);
+    const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
+    const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
+    const float c2 = p.c2, scale = p.scale;
+    // rows of dBD_raw nobody's rel_shift reads: BD_raw[0, 0 .. S-2] (the row the reshape drops)
+    if (qt == 0)
+      for (int j = threadIdx.x; j < S - 1; j += NUM_SM_WARPS * 32) dbd[j] = 0;
+    // delta_i = sum_c dO[i,c] O[i,c] over the head: each of the row's two threads takes half of the columns
+    float delta = 0.f;
+    if (row_ok) {
+      const uint4* a = reinterpret_cast<const uint4*>(p.dctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF);
+      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF);
+#pragma unroll
+      for (int u = 0; u < HALF / 8; u++) {
+        const uint4 x = __ldg(a + u), y = __ldg(o + u);
+        delta += bf_lo(x.x) * bf_lo(y.x) + bf_hi(x.x) * bf_hi(y.x) + bf_lo(x.y) * bf_lo(y.y) + bf_hi(x.y) * bf_hi(y.y) +
+                 bf_lo(x.z) * bf_lo(y.z) + bf_hi(x.z) * bf_hi(y.z) + bf_lo(x.w) * bf_lo(y.w) + bf_hi(x.w) * bf_hi(y.w);
+      }
+    }
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + (hh * 128 + row) * 4), "f"(delta) : "memory");
+    named_bar(1 + q, 64);
+    {
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(sRed + ((hh ^ 1) * 128 + row) * 4) : "memory");
+      delta += other;
+    }
+    const float lse = row_ok ? p.lse[(int64_t)bh * S + i] : 1e30f;
+    for (int t = 0; t < nkt; t++) {
+      const int st = t & 1;
+      const int j0 = t * 64 + 32 * hh;
+      // bias: two passes of 16 queries through the transposition buffer; lanes 0-15 / 16-31 pick up their row
+      uint32_t bw[16], kb[1];
+      load_bias_tile<32, 16>(G, i0 + q * 32, j0, S, p.ld, tbuf, lane, lane & 15, lane < 16, bw);
+      load_bias_tile<32, 16>(G, i0 + q * 32 + 16, j0, S, p.ld, tbuf, lane, lane & 15, lane >= 16, bw);
+      key_bits<32>(km, j0, S, lane, kb);
+      mbar_wait(s_full(st), (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[32], dp[32];
+      tmem_ld32(tmem_base + 64u * st + lane_t + 32u * hh, s);
+      tmem_ld32(tmem_base + 128u + 64u * st + lane_t + 32u * hh, dp);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(st));
+      uint32_t rw[16];
+      if (dr.on) drop_words<32>(dr, drow + (unsigned long long)j0, rw);
+      uint32_t pdw[16], dsw[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = 2 * k + e;
+          const float bias = e ? bf_hi(bw[k]) : bf_lo(bw[k]);
+          const float x = (__uint_as_float(s[c]) + bias) * c2;
+          const bool valid = ((kb[0] >> c) & 1u) != 0;
+          float P = valid ? ex2(x - lse) : 0.f;
+          float g = __uint_as_float(dp[c]);
+          float Pd = P;
+          if (dr.on) {
+            const bool keep = (e ? (rw[k] >> 16) : (rw[k] & 0xFFFFu)) >= dr.thr;
+            Pd = keep ? P * dr.inv_keep : 0.f;
+            g = keep ? g * dr.inv_keep : 0.f;
+          }
+          pv[e] = Pd;
+          dv[e] = P * (g - delta) * scale;
+        }
+        pdw[k] = pack_bf16(pv[0], pv[1]);
+        dsw[k] = pack_bf16(dv[0], dv[1]);
+      }
+      // ---- Pd and dBD_raw to HBM: thread-per-query registers -> transposition buffer -> lanes along the key axis ----
+      auto scatter = [&](const uint32_t (&w)[16], const bool shifted) {   // plain index map (Pd) or rel_shift^T (dBD_raw)
+#pragma unroll
+        for (int half = 0; half < 2; half++) {        // 16 queries at a time
+          if ((lane >> 4) == half) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 80 + 16 * c), "r"(w[4 * c]),
+                           "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                           : "memory");
+          }
+          __syncwarp();
+          const int j = j0 + lane;
+#pragma unroll 4
+          for (int r = 0; r < 16; r++) {
+            const int ii = i0 + q * 32 + half * 16 + r;
+            unsigned short v;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + r * 80 + 2 * lane) : "memory");
+            if (!shifted) {
+              if (ii < S && j < S) pdo[(int64_t)ii * p.ld + j] = v;
+            } else {
+              const int64_t dst = shift_src(ii, j, S, p.ld);
+              if (dst >= 0) dbd[dst] = v;
+            }
+          }
+          __syncwarp();
+        }
+      };
+      scatter(pdw, false);
+      scatter(dsw, true);
+      // ---- dS operand tile (128 queries x 64 keys, K-major, 128-byte swizzle) ----
+      if (t > 0) mbar_wait(ds_empty, (t - 1) & 1);   // dQu MMA and the dS store of the previous tile are done with it
+      const uint32_t drow_s = sDS + row * 128;
+      const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow_s + (((4 * hh + u) ^ sw) << 4)), "r"(dsw[4 * u]),
+                     "r"(dsw[4 * u + 1]), "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
+                     : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    // ---- epilogue: d(q+u) -> dqkv4[:, :, h*dk ...] ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* qrow = p.dq + ((int64_t)b * S + i) * (4 * (int64_t)D) + h * DK + hh * HALF;
+#pragma unroll
+    for (int g = 0; g < HALF / 32; g++) {
+      uint32_t o[32];
+      tmem_ld32(tmem_dQ + lane_t + (uint32_t)(hh * HALF + g * 32), o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * u]), __uint_as_float(o[8 * u + 1]));
+          v.y = pack_bf16(__uint_as_float(o[8 * u + 2]), __uint_as_float(o[8 * u + 3]));
+          v.z = pack_bf16(__uint_as_float(o[8 * u + 4]), __uint_as_float(o[8 * u + 5]));
+          v.w = pack_bf16(__uint_as_float(o[8 * u + 6]), __uint_as_float(o[8 * u + 7]));
+          *reinterpret_cast<uint4*>(qrow + g * 32 + 8 * u) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool qkv_map(CUtensorMap* m, const void* base, int B, int S, int row_elems) {
+  const int64_t dims[4] = {row_elems, S, B, 1}, str[3] = {row_elems, (int64_t)S * row_elems, (int64_t)S * row_elems};
+  const int box[4] = {64, 64, 1, 1};
+  return encode_map(m, base, dims, str, box);
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return A3T_ERR_CUDA;
+  }
+  return A3T_OK;
+}
+
+static int launch(const void* fn, int grid, int smem, cudaStream_t st, void** args, const char* what) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+  if (e != cudaSuccess) {
+    set_error("%s: launch: %s", what, cudaGetErrorString(e));
+    return A3T_ERR_CUDA;
+  }
+  return check_launch(what);
+}
+
+}  // namespace fa
+}  // namespace a3t
+
+using namespace a3t;
+
+extern "C" int a3t_attn_fused_supported(int B, int H, int S, int D) {
+  if (B < 1 || H < 1 || S < 1 || D < 1 || D % H) return 0;
+  const int dk = D / H;
+  if (dk != 64 && dk != 128 && dk != 192) return 0;
+  if ((int64_t)B * H * S * S >= ((int64_t)1 << 32)) return 0;   // dropout element index stays 32-bit inside a row block
+  return tc::get_encode() ? 1 : 0;
+}
+
+static int check_common(const char* what, const void* qkv4, const void* bd_raw, const uint8_t* keymask, int B, int H, int S,
+                        int D, int64_t ld, float drop_p, const unsigned long long* seed) {
+  A3T_REQUIRE(qkv4 && bd_raw && keymask, "%s: null pointer", what);
+  A3T_REQUIRE(a3t_attn_fused_supported(B, H, S, D), "%s: unsupported shape (B=%d H=%d S=%d D=%d; dk must be 64/128/192)", what, B,
+              H, S, D);
+  A3T_REQUIRE(ld >= S, "%s: row pitch %lld < S", what, (long long)ld);
+  A3T_REQUIRE((((uintptr_t)qkv4) & 15) == 0 && (D % 8) == 0, "%s: qkv4 must be 16-byte aligned", what);
+  A3T_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed), "%s: bad dropout arguments", what);
+  return A3T_OK;
+}
+
+extern "C" int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, void* ctx,
+                                   float* lse, int B, int H, int S, int D, float scale, float drop_p,
+                                   const unsigned long long* seed, uint32_t site, void* stream) {
+  using namespace fa;
+  int rc = check_common("relpos_attn_fwd", qkv4, bd_raw, keymask, B, H, S, D, ld, drop_p, seed);
+  if (rc) return rc;
+  A3T_REQUIRE(ctx && lse && (((uintptr_t)ctx) & 15) == 0, "relpos_attn_fwd: ctx / lse");
+  const int dk = D / H;
+  CUtensorMap tm;
+  A3T_REQUIRE(qkv_map(&tm, qkv4, B, S, 4 * D), "relpos_attn_fwd: tensor map");
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.bd_raw = (const __nv_bfloat16*)bd_raw; p.keymask = keymask; p.seed = seed; p.lse = lse; p.ctx = (__nv_bfloat16*)ctx;
+  p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
+  p.site = site;
+  const int nc = dk / 64;
+  const int smem = 1024 + 3 * nc * 16384 + 32768 + NUM_SM_WARPS * 32 * 144 + 2048 + 128;
+  const int grid = B * H * ((S + BM - 1) / BM);
+  void* args[2] = {&tm, &p};
+  const void* fn = dk == 192 ? (const void*)attn_fwd_kernel<192> : dk == 128 ? (const void*)attn_fwd_kernel<128> : (const void*)attn_fwd_kernel<64>;
+  static bool attr[3] = {false, false, false};
+  if (!attr[nc - 1]) {
+    rc = dk == 192 ? set_smem(attn_fwd_kernel<192>, SMEM_MAX, "relpos_attn_fwd")
+                   : dk == 128 ? set_smem(attn_fwd_kernel<128>, SMEM_MAX, "relpos_attn_fwd") : set_smem(attn_fwd_kernel<64>, SMEM_MAX, "relpos_attn_fwd");
+    if (rc) return rc;
+    attr[nc - 1] = true;
+  }
+  return launch(fn, grid, smem, (cudaStream_t)stream, args, "relpos_attn_fwd");
+}
+
+extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, const void* ctx,
+                                   const void* dctx, const float* lse, void* dqkv4, void* pd, void* ds, void* dbd, int B, int H,
+                                   int S, int D, float scale, float drop_p, const unsigned long long* seed, uint32_t site,
+                                   void* stream) {
+  using namespace fa;
+  int rc = check_common("relpos_attn_bwd", qkv4, bd_raw, keymask, B, H, S, D, ld, drop_p, seed);
+  if (rc) return rc;
+  A3T_REQUIRE(ctx && dctx && lse && dqkv4 && pd && ds && dbd, "relpos_attn_bwd: null pointer");
+  A3T_REQUIRE(((((uintptr_t)ctx) | ((uintptr_t)dctx) | ((uintptr_t)dqkv4) | ((uintptr_t)ds)) & 15) == 0 && (ld % 8) == 0,
+              "relpos_attn_bwd: 16-byte alignment / pitch multiple of 8");
+  const int dk = D / H;
+  CUtensorMap tmQ, tmDO, tmDS;
+  A3T_REQUIRE(qkv_map(&tmQ, qkv4, B, S, 4 * D) && qkv_map(&tmDO, dctx, B, S, D), "relpos_attn_bwd: tensor map");
+  {
+    const int64_t dims[4] = {S, S, H, B}, str[3] = {ld, (int64_t)S * ld, (int64_t)H * S * ld};
+    const int box[4] = {64, 128, 1, 1};
+    A3T_REQUIRE(tc::encode_map(&tmDS, ds, dims, str, box), "relpos_attn_bwd: dS tensor map");
+  }
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.bd_raw = (const __nv_bfloat16*)bd_raw; p.keymask = keymask; p.seed = seed; p.lse = const_cast<float*>(lse);
+  p.ctx = (__nv_bfloat16*)const_cast<void*>(ctx); p.dctx = (const __nv_bfloat16*)dctx; p.dq = (__nv_bfloat16*)dqkv4;
+  p.pd = (__nv_bfloat16*)pd; p.dbd = (__nv_bfloat16*)dbd;
+  p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
+  p.site = site;
+  const int nc = dk / 64;
+  const int smem = 1024 + 2 * nc * 16384 + 4 * nc * 8192 + 16384 + NUM_SM_WARPS * 16 * 80 + 1024 + 128;
+  const int grid = B * H * ((S + BM - 1) / BM);
+  void* args[4] = {&tmQ, &tmDO, &tmDS, &p};
+  const void* fn = dk == 192 ? (const void*)attn_bwd_kernel<192> : dk == 128 ? (const void*)attn_bwd_kernel<128> : (const void*)attn_bwd_kernel<64>;
+  static bool attr[3] = {false, false, false};
+  if (!attr[nc - 1]) {
+    rc = dk == 192 ? set_smem(attn_bwd_kernel<192>, SMEM_MAX, "relpos_attn_bwd")
+                   : dk == 128 ? set_smem(attn_bwd_kernel<128>, SMEM_MAX, "relpos_attn_bwd") : set_smem(attn_bwd_kernel<64>, SMEM_MAX, "relpos_attn_bwd");
+    if (rc) return rc;
+    attr[nc - 1] = true;
+  }
+  return launch(fn, grid, smem, (cudaStream_t)stream, args, "relpos_attn_bwd");
+}

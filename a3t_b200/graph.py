@@ -211,20 +211,28 @@ def _mha_fwd(ops, P, wc, pre, x, pos_d, keymask, cfg_H, p_drop, p_att, sites, tr
     h, mean, rstd = ops.ln_fwd(x, P[f"{pre}.norm_mha.weight"], P[f"{pre}.norm_mha.bias"], 1e-12)
     qkv4 = ops.conv_fwd(h, w4, b4)
     pp = ops.conv_fwd(pos_d.unsqueeze(0), wpos, None).squeeze(0)
-    ac, bd = ops.attn_scores_fwd(qkv4, pp, cfg_H)
-    Pm, Pd = ops.relpos_softmax_fwd(ac, bd, keymask, 1.0 / math.sqrt(D // cfg_H), drop=_drop(p_att, s_att, training))
-    del ac, bd
-    cx = ops.attn_pv_fwd(Pd, qkv4, cfg_H)
+    scale = 1.0 / math.sqrt(D // cfg_H)
+    fused = hasattr(ops, "attn_fused_ok") and ops.attn_fused_ok(x.shape[0], cfg_H, x.shape[1], D)
+    if fused:
+        # tcgen05 kernels that keep the scores on chip; BD_raw and the row log-sum-exp are what the backward needs
+        cx, bd, lse = ops.attn_fwd_fused(qkv4, pp, keymask, cfg_H, scale, drop=_drop(p_att, s_att, training))
+        ctx.update({"mha.bd": bd, "mha.lse": lse, "mha.keymask": keymask})
+    else:
+        ac, bd = ops.attn_scores_fwd(qkv4, pp, cfg_H)
+        Pm, Pd = ops.relpos_softmax_fwd(ac, bd, keymask, scale, drop=_drop(p_att, s_att, training))
+        del ac, bd
+        cx = ops.attn_pv_fwd(Pd, qkv4, cfg_H)
+        ctx.update({"mha.P": Pm, "mha.Pd": Pd})
     y = ops.conv_fwd(cx, wo, P[f"{a}.linear_out.bias"], drop=_drop(p_drop, s_out, training), residual=x)
     ctx.update({"mha.x": x, "mha.mean": mean, "mha.rstd": rstd, "mha.h": h, "mha.qkv4": qkv4, "mha.pp": pp,
-                "mha.P": Pm, "mha.Pd": Pd, "mha.cx": cx, "mha.s_att": s_att, "mha.s_out": s_out})
+                "mha.cx": cx, "mha.s_att": s_att, "mha.s_out": s_out, "mha.fused": fused})
     return y
 
 
 def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G, gpre=None, nxt=None):
     a = f"{pre}.self_attn"
     x, h, qkv4, pp = ctx["mha.x"], ctx["mha.h"], ctx["mha.qkv4"], ctx["mha.pp"]
-    Pm, Pd, cx = ctx["mha.P"], ctx["mha.Pd"], ctx["mha.cx"]
+    cx = ctx["mha.cx"]
     D = x.shape[-1]
     H = cfg_H
     w4, _ = wc.packed(ops, f"{a}.qkv4", [P[n] for n in [f"{a}.linear_q.weight", f"{a}.linear_k.weight",
@@ -238,11 +246,16 @@ def _mha_bwd(ops, P, wc, pre, dy, pos_d, cfg_H, p_drop, p_att, training, ctx, G,
     G.wgrad(ops, f"{a}.linear_out.weight", g, cx, 1)
     dcx = ops.conv_dgrad(g, wo)
     dqkv4 = torch.empty_like(qkv4)
-    dPd = ops.attn_pv_bwd(dcx, Pd, qkv4, H, dqkv4)
-    dS, dBD = ops.relpos_softmax_bwd(dPd, Pm, 1.0 / math.sqrt(D // H), drop=_drop(p_att, ctx["mha.s_att"], training))
-    del dPd
-    dpp = ops.attn_scores_bwd(dS, dBD, qkv4, pp, H, dqkv4)
-    del dS, dBD
+    if ctx["mha.fused"]:
+        dpp = ops.attn_bwd_fused(dcx, cx, ctx["mha.lse"], ctx["mha.bd"], qkv4, pp, ctx["mha.keymask"], H,
+                                 1.0 / math.sqrt(D // H), dqkv4, drop=_drop(p_att, ctx["mha.s_att"], training))
+    else:
+        Pm, Pd = ctx["mha.P"], ctx["mha.Pd"]
+        dPd = ops.attn_pv_bwd(dcx, Pd, qkv4, H, dqkv4)
+        dS, dBD = ops.relpos_softmax_bwd(dPd, Pm, 1.0 / math.sqrt(D // H), drop=_drop(p_att, ctx["mha.s_att"], training))
+        del dPd, Pm, Pd
+        dpp = ops.attn_scores_bwd(dS, dBD, qkv4, pp, H, dqkv4)
+        del dS, dBD
     G.wgrad(ops, f"{a}.linear_pos.weight", ops.cast_act(dpp).unsqueeze(0), pos_d.unsqueeze(0), 1)
     db4 = ops.colsum(dqkv4)
     dw4 = ops.conv_wgrad(dqkv4, h, 1).squeeze(-1)

@@ -185,6 +185,27 @@ int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, const int64_t*
                            float drop_p, const unsigned long long* seed, uint32_t site_speech,
                            uint32_t site_text, int V, int nseg, void* stream);
 
+/* Fused legacy relative-position attention (tcgen05; csrc/attn_fused.cu) -- replaces the matmul / rel_shift /
+ * softmax / dropout / matmul chain of transformer/attention.py:190-209 and its autograd backward without
+ * materialising AC, P or dP.
+ *   qkv4   (B,S,4D) bf16 = [q+u | q+v | k | v]            bd_raw (B,H,S,ld) bf16 = (q+v) p^T (from a3t_gemm)
+ *   keymask (B,S) uint8, 1 = valid key                     scale = 1/sqrt(D/H)
+ * fwd: ctx (B,S,D) bf16 = dropout(softmax((q+u)k^T + rel_shift(bd_raw)) * scale, masked) v;  lse (B,H,S) fp32 =
+ *      log2-domain log-sum-exp of the scaled scores (1e30 for a row without a valid key).
+ * bwd: given dctx (B,S,D) bf16: d(q+u) -> dqkv4[..., h*dk ..] (columns [0,D) of the (B,S,4D) bf16 buffer), and the
+ *      operands of the remaining contractions, each written once, (B,H,S,ld) bf16: pd = dropped probabilities,
+ *      ds = d scores (scaled), dbd = rel_shift^T(ds) (= d bd_raw).  ld % 8 == 0.
+ * Dropout element index = ((b*H + h)*S + i)*S + j (the contiguous (B,H,S,S) view), as the unfused kernels use.
+ * a3t_attn_fused_supported: 1 if (B,H,S,D) qualifies (D/H in {64,128,192}, B*H*S*S < 2^32). */
+int a3t_attn_fused_supported(int B, int H, int S, int D);
+int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, void* ctx,
+                        float* lse, int B, int H, int S, int D, float scale, float drop_p,
+                        const unsigned long long* seed, uint32_t site, void* stream);
+int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask,
+                        const void* ctx, const void* dctx, const float* lse, void* dqkv4, void* pd, void* ds,
+                        void* dbd, int B, int H, int S, int D, float scale, float drop_p,
+                        const unsigned long long* seed, uint32_t site, void* stream);
+
 /* Legacy relative-position masked softmax (transformer/attention.py:145-165 rel_shift, :205-207
  * scale, :79-86 finfo.min fill / softmax / zero fill, :88 dropout).
  *   s[i,j] = (AC[i,j] + BDraw_shifted[i,j]) * scale ; key j invalid -> finfo(f32).min
