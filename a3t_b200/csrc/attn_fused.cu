@@ -70,53 +70,17 @@ __device__ __forceinline__ int64_t shift_src(int i, int j, int S, int64_t ld) {
   return j <= i ? (int64_t)i * ld + (S - 1 - i) + j : (int64_t)(i + 1) * ld - (i + 2) + j;
 }
 
-// Bias sub-tile (ROWS queries x COLS keys) of this warp: coalesced loads (lane = key), transposition through tbuf
-// (pitch COLS*2+16 bytes), thread = query read-back of COLS bf16 packed in COLS/2 words.  Rows: i_first .. +ROWS-1
-// are stored at buffer rows 0..ROWS-1; the caller's lane reads buffer row `myrow` (< ROWS) if `mine`.
-template <int COLS, int ROWS>
-__device__ __forceinline__ void load_bias_tile(const __nv_bfloat16* __restrict__ G, int i_first, int j_first, int S, int64_t ld,
-                                               uint32_t tbuf, int lane, int myrow, bool mine, uint32_t (&out)[COLS / 2]) {
-  constexpr int PITCH = COLS * 2 + 16;
-  constexpr int PER = COLS / 32;  // keys per lane per row
-  const unsigned short* Gs = reinterpret_cast<const unsigned short*>(G);
-#pragma unroll 1
-  for (int r0 = 0; r0 < ROWS; r0 += 8) {
-    unsigned short v[8][PER];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int i = i_first + r0 + r;
-#pragma unroll
-      for (int e = 0; e < PER; e++) {
-        const int64_t src = shift_src(i, j_first + lane + 32 * e, S, ld);
-        v[r][e] = src >= 0 ? __ldg(Gs + src) : (unsigned short)0;
-      }
+// validity bits of all keys of utterance b into shared memory (word w, bit e = key 32 w + e is a real key)
+__device__ __forceinline__ void build_key_bits(const uint8_t* __restrict__ km, int S, uint32_t sKB, int tid, int nthreads) {
+  const int nwords = (S + 31) / 32 + 4;   // tiles read up to 128 keys past the last valid one
+  for (int w = tid; w < nwords; w += nthreads) {
+    uint32_t bits = 0;
+#pragma unroll 4
+    for (int e = 0; e < 32; e++) {
+      const int j = 32 * w + e;
+      if (j < S && km[j] != 0) bits |= 1u << e;
     }
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-      for (int e = 0; e < PER; e++)
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(tbuf + (r0 + r) * PITCH + 2 * (lane + 32 * e)), "h"(v[r][e]) : "memory");
-  }
-  __syncwarp();
-  if (mine) {
-#pragma unroll
-    for (int c = 0; c < COLS / 8; c++)
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(out[4 * c]), "=r"(out[4 * c + 1]), "=r"(out[4 * c + 2]), "=r"(out[4 * c + 3])
-                   : "r"(tbuf + myrow * PITCH + 16 * c)
-                   : "memory");
-  }
-  __syncwarp();
-}
-
-// validity bits of COLS keys starting at j_first (bit c = key j_first + c is a real, non-padded key)
-template <int COLS>
-__device__ __forceinline__ void key_bits(const uint8_t* __restrict__ km, int j_first, int S, int lane, uint32_t (&bits)[COLS / 32]) {
-#pragma unroll
-  for (int e = 0; e < COLS / 32; e++) {
-    const int j = j_first + 32 * e + lane;
-    const bool ok = j < S && km[j] != 0;
-    bits[e] = __ballot_sync(0xffffffffu, ok);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sKB + 4 * w), "r"(bits) : "memory");
   }
 }
 
@@ -136,23 +100,49 @@ __device__ __forceinline__ void drop_words(const Drop& dr, unsigned long long id
   }
 }
 
+// The rel_shift bias of a (16 queries x COLS keys) sub-tile arrives by TMA as a box of 16 rows x (COLS + 24) columns of
+// BD_raw: the band a tile needs is a parallelogram (one element of skew per query), and TMA wants the first column
+// of a box 16-byte aligned, so the box starts `sft` (0..7) elements early: row r holds the COLS values of its query
+// from element (15 - r + sft) on.  Thread = query reads its window as aligned words and re-aligns it with a funnel
+// shift: word k of the result = elements (2k, 2k+1) of the thread's column half.
+__device__ __forceinline__ int box_col0(int S, int i_first, int j0, bool upper) {
+  // first column query (i_first + 15) needs: rel_shift reads BD_raw[i, S-1-i+j] below the diagonal (j <= i) and
+  // BD_raw[i+1, j-i-2] above it (j >= i+2; the box is then anchored one row lower)
+  return upper ? j0 - (i_first + 15) - 2 : S - 1 - (i_first + 15) + j0;
+}
+template <int COLS, int HCOLS>   // COLS: keys per tile; HCOLS: keys per thread (column half)
+__device__ __forceinline__ void read_bias_window(uint32_t boxes, int sft, int lane, int hh, uint32_t (&out)[HCOLS / 2]) {
+  constexpr int PITCH = (COLS + 24) * 2;
+  const int r = lane & 15;
+  const int e0 = 15 - r + sft + HCOLS * hh;
+  const uint32_t a = boxes + (lane >> 4) * (16 * PITCH) + r * PITCH + 4 * (e0 >> 1);
+  const uint32_t sh = (uint32_t)(e0 & 1) * 16u;
+  uint32_t w[HCOLS / 2 + 1];
+#pragma unroll
+  for (int k = 0; k <= HCOLS / 2; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(a + 4 * k) : "memory");
+#pragma unroll
+  for (int k = 0; k < HCOLS / 2; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================
 template <int DK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ Params p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBD,
+                const __grid_constant__ Params p) {
   A3T_PDL_TRIGGER();
   constexpr int NC = DK / 64;                  // 64-wide chunks of the head dimension
   constexpr uint32_t QB = NC * 16384u;         // one 128 x DK bf16 operand tile
-  constexpr int T_BYTES = 32 * 144;
+  constexpr uint32_t BOX = 16 * 152 * 2;       // bias box of one 16-query group (128 keys + 15 of skew + 7 of alignment)
   constexpr int HALF = DK / 2;                 // O columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + QB, sV = sK + QB, sP = sV + QB, sT = sP + 32768u, sRed = sT + NUM_SM_WARPS * T_BYTES,
-                 sBar = sRed + 2048u;
+  const uint32_t sQ = base, sK = sQ + QB, sV = sK + QB, sP = sV + QB, sB = sP + 32768u, sRed = sB + 8 * BOX, sKB = sRed + 2048u,
+                 sBar = sKB + 1024u;
   const uint32_t q_full = sBar, k_full = sBar + 8, k_empty = sBar + 16, v_full = sBar + 24, v_empty = sBar + 32,
-                 p_full = sBar + 72, p_empty = sBar + 80, o_full = sBar + 88, tmem_slot = sBar + 96;
+                 p_full = sBar + 72, p_empty = sBar + 80, o_full = sBar + 88, tmem_slot = sBar + 96, b_full = sBar + 104,
+                 b_empty = sBar + 112;
   auto s_full = [&](int i) { return sBar + 40u + 8u * i; };
   auto s_empty = [&](int i) { return sBar + 56u + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,9 +154,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (warp == PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBD) : "memory");
     mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(s_empty(0), NUM_SM_WARPS); mbar_init(s_empty(1), NUM_SM_WARPS);
     mbar_init(p_full, NUM_SM_WARPS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    mbar_init(b_full, 1); mbar_init(b_empty, NUM_SM_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -187,6 +179,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_expect_tx(q_full, QB);
       for (int c = 0; c < NC; c++)
         for (int r = 0; r < 2; r++) tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
+      int nb = 0;   // bias loads issued
+      auto load_bias = [&](int j0, bool upper) {
+        if (nb > 0) mbar_wait(b_empty, (nb - 1) & 1);
+        mbar_expect_tx(b_full, 8 * BOX);
+        for (int g = 0; g < 8; g++) {
+          const int i_first = i0 + 16 * g;
+          tma_load_4d(sB + g * BOX, &tmBD, b_full, box_col0(S, i_first, j0, upper) & ~7, i_first + (upper ? 1 : 0), h, b);
+        }
+        nb++;
+      };
       for (int t = 0; t < nkt; t++) {
         const int j0 = t * 128;
         if (t > 0) mbar_wait(k_empty, (t - 1) & 1);
@@ -194,11 +196,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int c = 0; c < NC; c++)
           for (int r = 0; r < 2; r++)
             tma_load_4d(sK + c * 16384 + r * 8192, &tmQKV, k_full, 2 * D + h * DK + 64 * c, j0 + 64 * r, b, 0);
+        load_bias(j0, t > qt);          // t < qt: below the diagonal; t == qt: the lower part first
         if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
         mbar_expect_tx(v_full, QB);
         for (int kc = 0; kc < 2; kc++)   // V as the MN-major B operand of P V: per 64-key chunk, NC atoms of 64 head columns
           for (int a = 0; a < NC; a++)
             tma_load_4d(sV + kc * (NC * 8192) + a * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * a, j0 + 64 * kc, b, 0);
+        if (t == qt) load_bias(j0, true);   // the diagonal tile also needs the part above the diagonal
       }
     }
   } else if (warp == MMA_WARP) {
@@ -244,19 +248,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ===================================== softmax warps ====================================
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane, i = i0 + row;
-    const uint32_t tbuf = sT + warp * T_BYTES;
-    const __nv_bfloat16* G = p.bd_raw + (int64_t)bh * S * p.ld;
     const uint8_t* km = p.keymask + (int64_t)b * S;
+    build_key_bits(km, S, sKB, threadIdx.x, NUM_SM_WARPS * 32);
+    named_bar(5, NUM_SM_WARPS * 32);
     const Drop dr = make_drop(p.drop_p, p.seed, p.site);
     const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
     const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
     float m = -INFINITY, l = 0.f;
     const float c2 = p.c2;
+    int nb = 0;   // bias boxes consumed
+    auto take_bias = [&](uint32_t (&w)[32], int jt, bool upper) {
+      mbar_wait(b_full, nb & 1);
+      read_bias_window<128, 64>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, hh, w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_empty);
+      nb++;
+    };
     for (int t = 0; t < nkt; t++) {
       const int j0 = t * 128 + 64 * hh;
       uint32_t bw[32], kb[2];
-      load_bias_tile<64, 32>(G, i0 + q * 32, j0, S, p.ld, tbuf, lane, lane, true, bw);
-      key_bits<64>(km, j0, S, lane, kb);
+      take_bias(bw, t * 128, t > qt);
+      if (t == qt) {   // diagonal tile: keys j <= i from the lower band, j >= i + 2 from the upper one, j == i + 1 is the zero
+        uint32_t up[32];
+        take_bias(up, t * 128, true);
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+          const int ja = j0 + 2 * k, jb = ja + 1;
+          const uint32_t lo16 = ja <= i ? (bw[k] & 0xFFFFu) : (ja == i + 1 ? 0u : (up[k] & 0xFFFFu));
+          const uint32_t hi16 = jb <= i ? (bw[k] & 0xFFFF0000u) : (jb == i + 1 ? 0u : (up[k] & 0xFFFF0000u));
+          bw[k] = lo16 | hi16;
+        }
+      } else if (j0 == i + 1) {   // first key of the tile right of the diagonal, last query of the tile
+        bw[0] &= 0xFFFF0000u;
+      }
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(kb[0]), "=r"(kb[1]) : "r"(sKB + (uint32_t)(j0 >> 5) * 4u) : "memory");
       mbar_wait(s_full(t & 1), (t >> 1) & 1);
       tc_fence_after();
       uint32_t s[64];
@@ -380,43 +405,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // ================================================================================================
 // backward
 // ================================================================================================
-// 64-key tiles.  Shared memory: Qu and dO resident (2 x 128 x DK), K and V double buffered (2 x 2 x 64 x DK), the dS
-// operand tile (128 x 64), per-warp transposition buffers.  TMEM: S and dP double buffered (4 x 64 columns), dQu (DK).
+// 64-key tiles.  Shared memory: Qu and dO resident (2 x 128 x DK), K double buffered and V single buffered (3 x 64 x DK),
+// the dS operand tile and the Pd staging tile (2 x 128 x 64), the bias boxes.  TMEM: S and dP double buffered
+// (4 x 64 columns), dQu (DK).  Warp 10 issues the TMA tensor stores of dS and Pd.
+constexpr int STORE_WARP = 10;
+constexpr int NUM_THREADS_BWD = NUM_THREADS + 32;
+
 template <int DK>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS_BWD, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ Params p) {
+                const __grid_constant__ CUtensorMap tmBD, const __grid_constant__ CUtensorMap tmDS,
+                const __grid_constant__ CUtensorMap tmPD, const __grid_constant__ Params p) {
   A3T_PDL_TRIGGER();
   constexpr int NC = DK / 64;
   constexpr uint32_t QB = NC * 16384u;         // 128 x DK
   constexpr uint32_t KB = NC * 8192u;          // 64 x DK
-  constexpr int T_BYTES = 16 * 80;             // 16 rows x (32 keys * 2 B + 16)
+  constexpr uint32_t BOX = 16 * 88 * 2;        // bias box of one 16-query group (64 keys + 15 of skew + 7 of alignment)
   constexpr int HALF = DK / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sDO = sQ + QB, sK = sDO + QB, sV = sK + 2 * KB, sDS = sV + 2 * KB, sT = sDS + 16384u,
-                 sRed = sT + NUM_SM_WARPS * T_BYTES, sBar = sRed + 1024u;
-  const uint32_t q_full = sBar, ds_full = sBar + 8, ds_empty = sBar + 16, o_full = sBar + 24, tmem_slot = sBar + 32;
-  auto kv_full = [&](int i) { return sBar + 40u + 8u * i; };
-  auto kv_empty = [&](int i) { return sBar + 56u + 8u * i; };
-  auto s_full = [&](int i) { return sBar + 72u + 8u * i; };
-  auto s_empty = [&](int i) { return sBar + 88u + 8u * i; };
+  const uint32_t sQ = base, sDO = sQ + QB, sK = sDO + QB, sV = sK + 2 * KB, sDS = sV + KB, sPD = sDS + 16384u, sB = sPD + 16384u,
+                 sRed = sDS /* used once, before the first tile */, sKB = sB + 8 * BOX, sBar = sKB + 256u;
+  const uint32_t q_full = sBar, out_full = sBar + 8, out_empty = sBar + 16, o_full = sBar + 24, tmem_slot = sBar + 32,
+                 v_full = sBar + 40, v_empty = sBar + 48, b_full = sBar + 56, b_empty = sBar + 64;
+  auto k_full = [&](int i) { return sBar + 72u + 8u * i; };
+  auto k_empty = [&](int i) { return sBar + 88u + 8u * i; };
+  auto s_full = [&](int i) { return sBar + 104u + 8u * i; };
+  auto s_empty = [&](int i) { return sBar + 120u + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, H = p.H, D = p.D;
   const int nqt = (S + BM - 1) / BM, nkt = (S + 63) / 64;
   const int qt = blockIdx.x % nqt, bh = blockIdx.x / nqt;
   const int h = bh % H, b = bh / H;
   const int i0 = qt * BM;
+  // key tiles 2 qt and 2 qt + 1 straddle the diagonal of this query tile (both bands of BD_raw are needed)
+  auto is_diag = [&](int t) { return (t >> 1) == qt; };
 
   if (warp == PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDO) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDS) : "memory");
-    mbar_init(q_full, 1); mbar_init(ds_full, NUM_SM_WARPS); mbar_init(ds_empty, 1); mbar_init(o_full, 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBD) : "memory");
+    mbar_init(q_full, 1); mbar_init(out_full, NUM_SM_WARPS); mbar_init(out_empty, 2); mbar_init(o_full, 1);
+    mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(b_full, 1); mbar_init(b_empty, NUM_SM_WARPS);
     for (int i = 0; i < 2; i++) {
-      mbar_init(kv_full(i), 1); mbar_init(kv_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(s_empty(i), NUM_SM_WARPS);
+      mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(s_empty(i), NUM_SM_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == STORE_WARP && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDS) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmPD) : "memory");
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
@@ -439,14 +477,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
           tma_load_4d(sDO + c * 16384 + r * 8192, &tmDO, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
         }
+      int nb = 0;
+      auto load_bias = [&](int j0, bool upper) {
+        if (nb > 0) mbar_wait(b_empty, (nb - 1) & 1);
+        mbar_expect_tx(b_full, 8 * BOX);
+        for (int g = 0; g < 8; g++) {
+          const int i_first = i0 + 16 * g;
+          tma_load_4d(sB + g * BOX, &tmBD, b_full, box_col0(S, i_first, j0, upper) & ~7, i_first + (upper ? 1 : 0), h, b);
+        }
+        nb++;
+      };
       for (int t = 0; t < nkt; t++) {
         const int st = t & 1, j0 = t * 64;
-        if (t >= 2) mbar_wait(kv_empty(st), ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(kv_full(st), 2 * KB);
-        for (int c = 0; c < NC; c++) {
-          tma_load_4d(sK + st * KB + c * 8192, &tmQKV, kv_full(st), 2 * D + h * DK + 64 * c, j0, b, 0);
-          tma_load_4d(sV + st * KB + c * 8192, &tmQKV, kv_full(st), 3 * D + h * DK + 64 * c, j0, b, 0);
-        }
+        if (t >= 2) mbar_wait(k_empty(st), ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(k_full(st), KB);
+        for (int c = 0; c < NC; c++) tma_load_4d(sK + st * KB + c * 8192, &tmQKV, k_full(st), 2 * D + h * DK + 64 * c, j0, b, 0);
+        load_bias(j0, (t >> 1) > qt);
+        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
+        mbar_expect_tx(v_full, KB);
+        for (int c = 0; c < NC; c++) tma_load_4d(sV + c * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * c, j0, b, 0);
+        if (is_diag(t)) load_bias(j0, true);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -455,59 +505,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
       const uint64_t dQ = make_smem_desc(sQ, 16), dDO = make_smem_desc(sDO, 16), dDS = make_smem_desc(sDS, 16);
+      const uint64_t dV = make_smem_desc(sV, 16);
       auto issue_s = [&](int t) {
         const int st = t & 1;
-        mbar_wait(kv_full(st), (t >> 1) & 1);
+        mbar_wait(k_full(st), (t >> 1) & 1);
         if (t >= 2) mbar_wait(s_empty(st), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint64_t dK = make_smem_desc(sK + st * KB, 16), dV = make_smem_desc(sV + st * KB, 16);
+        const uint64_t dK = make_smem_desc(sK + st * KB, 16);
 #pragma unroll
         for (int c = 0; c < NC; c++)
 #pragma unroll
           for (int k = 0; k < 4; k++)
             umma_bf16(tmem_base + 64u * st, dQ + (uint64_t)((c * 16384 + k * 32) >> 4), dK + (uint64_t)((c * 8192 + k * 32) >> 4),
                       idesc_s, (c | k) ? 1u : 0u);
+        mbar_wait(v_full, t & 1);
+        tc_fence_after();
 #pragma unroll
         for (int c = 0; c < NC; c++)
 #pragma unroll
           for (int k = 0; k < 4; k++)
             umma_bf16(tmem_base + 128u + 64u * st, dDO + (uint64_t)((c * 16384 + k * 32) >> 4),
                       dV + (uint64_t)((c * 8192 + k * 32) >> 4), idesc_s, (c | k) ? 1u : 0u);
+        umma_commit(v_empty);
         umma_commit(s_full(st));
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int t = 0; t < nkt; t++) {
         if (t + 1 < nkt) issue_s(t + 1);
-        mbar_wait(ds_full, t & 1);
+        mbar_wait(out_full, t & 1);
         tc_fence_after();
         // dQu += dS (128 x 64 keys, K-major) * K (64 keys x DK: the K tile read MN-major, NC atoms 8 KB apart)
         const uint64_t dKm = make_smem_desc(sK + (t & 1) * KB, 8192);
 #pragma unroll
         for (int k = 0; k < 4; k++)
           umma_bf16(tmem_dQ, dDS + (uint64_t)((k * 32) >> 4), dKm + (uint64_t)((k * 2048) >> 4), idesc_q, (t | k) ? 1u : 0u);
-        // the same shared-memory tile goes to HBM as dS (for dK = dS^T (q+u)); its reads must finish before reuse
+        umma_commit(k_empty(t & 1));
+        umma_commit(out_empty);
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp == STORE_WARP) {
+    // dS (for dK = dS^T (q+u)) and Pd (for dV = Pd^T dO) leave through TMA tensor stores of the two staging tiles
+    if (elect_one()) {
+      for (int t = 0; t < nkt; t++) {
+        mbar_wait(out_full, t & 1);
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)&tmDS),
                      "r"(sDS), "r"(t * 64), "r"(i0), "r"(h), "r"(b)
                      : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)&tmPD),
+                     "r"(sPD), "r"(t * 64), "r"(i0), "r"(h), "r"(b)
+                     : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        umma_commit(kv_empty(t & 1));
-        umma_commit(ds_empty);
+        mbar_arrive(out_empty);
       }
-      umma_commit(o_full);
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane, i = i0 + row;
     const bool row_ok = i < S;
-    const uint32_t tbuf = sT + warp * T_BYTES;
+    const int ld = (int)p.ld;
     const int64_t blk = (int64_t)bh * S * p.ld;
-    const __nv_bfloat16* G = p.bd_raw + blk;
     unsigned short* const dbd = reinterpret_cast<unsigned short*>(p.dbd + blk);
-    unsigned short* const pdo = reinterpret_cast<unsigned short*>(p.pd + blk);
     const uint8_t* km = p.keymask + (int64_t)b * S;
+    build_key_bits(km, S, sKB, threadIdx.x, NUM_SM_WARPS * 32);
     const Drop dr = make_drop(p.drop_p, p.seed, p.site);
     const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
     const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
@@ -528,21 +591,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + (hh * 128 + row) * 4), "f"(delta) : "memory");
-    named_bar(1 + q, 64);
+    named_bar(5, NUM_SM_WARPS * 32);   // key bits and the delta halves are visible
     {
       float other;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(sRed + ((hh ^ 1) * 128 + row) * 4) : "memory");
       delta += other;
     }
+    named_bar(5, NUM_SM_WARPS * 32);   // (the exchange area is the dS staging tile: everyone has read before anyone writes)
     const float lse = row_ok ? p.lse[(int64_t)bh * S + i] : 1e30f;
+    // scatter geometry of this warp's 32 queries (rel_shift^T): element (ii, j) -> dBD_raw offset arow + j (+ dl above the diagonal)
+    const int dl = ld - S - 1;
+    const uint32_t tbuf = sPD + q * 4096 + hh * 2048;   // transposition scratch inside this warp pair's rows of the Pd staging tile
+    int nb = 0;
+    auto take_bias = [&](uint32_t (&w)[16], int jt, bool upper) {
+      mbar_wait(b_full, nb & 1);
+      read_bias_window<64, 32>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, hh, w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_empty);
+      nb++;
+    };
     for (int t = 0; t < nkt; t++) {
       const int st = t & 1;
       const int j0 = t * 64 + 32 * hh;
-      // bias: two passes of 16 queries through the transposition buffer; lanes 0-15 / 16-31 pick up their row
-      uint32_t bw[16], kb[1];
-      load_bias_tile<32, 16>(G, i0 + q * 32, j0, S, p.ld, tbuf, lane, lane & 15, lane < 16, bw);
-      load_bias_tile<32, 16>(G, i0 + q * 32 + 16, j0, S, p.ld, tbuf, lane, lane & 15, lane >= 16, bw);
-      key_bits<32>(km, j0, S, lane, kb);
+      uint32_t bw[16], kb;
+      take_bias(bw, t * 64, (t >> 1) > qt);
+      if (is_diag(t)) {
+        uint32_t up[16];
+        take_bias(up, t * 64, true);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int ja = j0 + 2 * k, jb = ja + 1;
+          const uint32_t lo16 = ja <= i ? (bw[k] & 0xFFFFu) : (ja == i + 1 ? 0u : (up[k] & 0xFFFFu));
+          const uint32_t hi16 = jb <= i ? (bw[k] & 0xFFFF0000u) : (jb == i + 1 ? 0u : (up[k] & 0xFFFF0000u));
+          bw[k] = lo16 | hi16;
+        }
+      } else if (j0 == i + 1) {
+        bw[0] &= 0xFFFF0000u;
+      }
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kb) : "r"(sKB + (uint32_t)(j0 >> 5) * 4u) : "memory");
       mbar_wait(s_full(st), (t >> 1) & 1);
       tc_fence_after();
       uint32_t s[32], dp[32];
@@ -563,8 +649,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const int c = 2 * k + e;
           const float bias = e ? bf_hi(bw[k]) : bf_lo(bw[k]);
           const float x = (__uint_as_float(s[c]) + bias) * c2;
-          const bool valid = ((kb[0] >> c) & 1u) != 0;
-          float P = valid ? ex2(x - lse) : 0.f;
+          const bool valid = ((kb >> c) & 1u) != 0;
+          const float P = valid ? ex2(x - lse) : 0.f;
           float g = __uint_as_float(dp[c]);
           float Pd = P;
           if (dr.on) {
@@ -578,49 +664,49 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         pdw[k] = pack_bf16(pv[0], pv[1]);
         dsw[k] = pack_bf16(dv[0], dv[1]);
       }
-      // ---- Pd and dBD_raw to HBM: thread-per-query registers -> transposition buffer -> lanes along the key axis ----
-      auto scatter = [&](const uint32_t (&w)[16], const bool shifted) {   // plain index map (Pd) or rel_shift^T (dBD_raw)
+      // ---- outputs.  The staging tiles are free once the previous tile's dQu MMA and tensor stores have read them ----
+      if (t > 0) mbar_wait(out_empty, (t - 1) & 1);
+      // dBD_raw = rel_shift^T(dS): thread-per-query registers -> scratch -> lanes along the key axis, 2-byte stores
+      // (rows of dBD_raw shift by one element per query: no wider aligned store exists)
 #pragma unroll
-        for (int half = 0; half < 2; half++) {        // 16 queries at a time
-          if ((lane >> 4) == half) {
+      for (int half = 0; half < 2; half++) {        // 16 queries at a time
+        if ((lane >> 4) == half) {
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 80 + 16 * c), "r"(w[4 * c]),
-                           "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
-                           : "memory");
-          }
-          __syncwarp();
-          const int j = j0 + lane;
-#pragma unroll 4
-          for (int r = 0; r < 16; r++) {
-            const int ii = i0 + q * 32 + half * 16 + r;
-            unsigned short v;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + r * 80 + 2 * lane) : "memory");
-            if (!shifted) {
-              if (ii < S && j < S) pdo[(int64_t)ii * p.ld + j] = v;
-            } else {
-              const int64_t dst = shift_src(ii, j, S, p.ld);
-              if (dst >= 0) dbd[dst] = v;
-            }
-          }
-          __syncwarp();
+          for (int c = 0; c < 4; c++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 80 + 16 * c), "r"(dsw[4 * c]),
+                         "r"(dsw[4 * c + 1]), "r"(dsw[4 * c + 2]), "r"(dsw[4 * c + 3])
+                         : "memory");
         }
-      };
-      scatter(pdw, false);
-      scatter(dsw, true);
-      // ---- dS operand tile (128 queries x 64 keys, K-major, 128-byte swizzle) ----
-      if (t > 0) mbar_wait(ds_empty, (t - 1) & 1);   // dQu MMA and the dS store of the previous tile are done with it
-      const uint32_t drow_s = sDS + row * 128;
+        __syncwarp();
+        const int j = j0 + lane;
+        const int ii0 = i0 + q * 32 + half * 16;
+        int arow = ii0 * (ld - 1) + S - 1 + j;      // offset of (ii0, j) through the lower band
+#pragma unroll 8
+        for (int r = 0; r < 16; r++) {
+          const int ii = ii0 + r;
+          unsigned short v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + r * 80 + 2 * lane) : "memory");
+          if (ii < S && j < S && j != ii + 1) dbd[arow + (j > ii ? dl : 0)] = v;
+          arow += ld - 1;
+        }
+        __syncwarp();
+      }
+      named_bar(1 + q, 64);   // the partner warp's scratch lives in the same rows of the staging tile
       const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow_s + (((4 * hh + u) ^ sw) << 4)), "r"(dsw[4 * u]),
-                     "r"(dsw[4 * u + 1]), "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
+      for (int u = 0; u < 4; u++) {
+        const uint32_t off = row * 128 + (((4 * hh + u) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dsw[4 * u]), "r"(dsw[4 * u + 1]),
+                     "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
                      : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPD + off), "r"(pdw[4 * u]), "r"(pdw[4 * u + 1]),
+                     "r"(pdw[4 * u + 2]), "r"(pdw[4 * u + 3])
+                     : "memory");
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(out_full);
     }
     // ---- epilogue: d(q+u) -> dqkv4[:, :, h*dk ...] ----
     mbar_wait(o_full, 0);
@@ -672,7 +758,13 @@ static int set_smem(K kernel, int bytes, const char* what) {
   return A3T_OK;
 }
 
-static int launch(const void* fn, int grid, int smem, cudaStream_t st, void** args, const char* what) {
+static bool score_map(CUtensorMap* m, const void* base, int B, int H, int S, int64_t ld, int box_cols, int box_rows, bool swz) {
+  const int64_t dims[4] = {ld, S, H, B}, str[3] = {ld, (int64_t)S * ld, (int64_t)H * S * ld};
+  const int box[4] = {box_cols, box_rows, 1, 1};
+  return encode_map(m, base, dims, str, box, 2, swz);
+}
+
+static int launch(const void* fn, int grid, int threads, int smem, cudaStream_t st, void** args, const char* what) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -681,7 +773,7 @@ static int launch(const void* fn, int grid, int smem, cudaStream_t st, void** ar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
@@ -724,17 +816,20 @@ extern "C" int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t
   if (rc) return rc;
   A3T_REQUIRE(ctx && lse && (((uintptr_t)ctx) & 15) == 0, "relpos_attn_fwd: ctx / lse");
   const int dk = D / H;
-  CUtensorMap tm;
-  A3T_REQUIRE(qkv_map(&tm, qkv4, B, S, 4 * D), "relpos_attn_fwd: tensor map");
+  A3T_REQUIRE((ld % 8) == 0 && (((uintptr_t)bd_raw) & 15) == 0, "relpos_attn_fwd: bd_raw pitch %% 8 / alignment");
+  CUtensorMap tm, tmBD;
+  A3T_REQUIRE(qkv_map(&tm, qkv4, B, S, 4 * D) && score_map(&tmBD, bd_raw, B, H, S, ld, 152, 16, false),
+              "relpos_attn_fwd: tensor map");
   Params p;
   memset(&p, 0, sizeof(p));
   p.bd_raw = (const __nv_bfloat16*)bd_raw; p.keymask = keymask; p.seed = seed; p.lse = lse; p.ctx = (__nv_bfloat16*)ctx;
   p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
   p.site = site;
   const int nc = dk / 64;
-  const int smem = 1024 + 3 * nc * 16384 + 32768 + NUM_SM_WARPS * 32 * 144 + 2048 + 128;
+  A3T_REQUIRE(S <= 8000, "relpos_attn_fwd: S=%d exceeds the key-bit table", S);
+  const int smem = 1024 + 3 * nc * 16384 + 32768 + 8 * 16 * 152 * 2 + 2048 + 1024 + 128;
   const int grid = B * H * ((S + BM - 1) / BM);
-  void* args[2] = {&tm, &p};
+  void* args[3] = {&tm, &tmBD, &p};
   const void* fn = dk == 192 ? (const void*)attn_fwd_kernel<192> : dk == 128 ? (const void*)attn_fwd_kernel<128> : (const void*)attn_fwd_kernel<64>;
   static bool attr[3] = {false, false, false};
   if (!attr[nc - 1]) {
@@ -743,7 +838,7 @@ extern "C" int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t
     if (rc) return rc;
     attr[nc - 1] = true;
   }
-  return launch(fn, grid, smem, (cudaStream_t)stream, args, "relpos_attn_fwd");
+  return launch(fn, grid, NUM_THREADS, smem, (cudaStream_t)stream, args, "relpos_attn_fwd");
 }
 
 extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, const void* ctx,
@@ -757,12 +852,17 @@ extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t
   A3T_REQUIRE(((((uintptr_t)ctx) | ((uintptr_t)dctx) | ((uintptr_t)dqkv4) | ((uintptr_t)ds)) & 15) == 0 && (ld % 8) == 0,
               "relpos_attn_bwd: 16-byte alignment / pitch multiple of 8");
   const int dk = D / H;
-  CUtensorMap tmQ, tmDO, tmDS;
-  A3T_REQUIRE(qkv_map(&tmQ, qkv4, B, S, 4 * D) && qkv_map(&tmDO, dctx, B, S, D), "relpos_attn_bwd: tensor map");
+  A3T_REQUIRE(((((uintptr_t)bd_raw) | ((uintptr_t)pd)) & 15) == 0 && S <= 1900, "relpos_attn_bwd: alignment / S <= 1900");
+  CUtensorMap tmQ, tmDO, tmBD, tmDS, tmPD;
+  A3T_REQUIRE(qkv_map(&tmQ, qkv4, B, S, 4 * D) && qkv_map(&tmDO, dctx, B, S, D) &&
+                  score_map(&tmBD, bd_raw, B, H, S, ld, 88, 16, false),
+              "relpos_attn_bwd: tensor map");
   {
+    // stores clip at column S (not at the pitch): the pad columns of a row are never written
     const int64_t dims[4] = {S, S, H, B}, str[3] = {ld, (int64_t)S * ld, (int64_t)H * S * ld};
     const int box[4] = {64, 128, 1, 1};
-    A3T_REQUIRE(tc::encode_map(&tmDS, ds, dims, str, box), "relpos_attn_bwd: dS tensor map");
+    A3T_REQUIRE(tc::encode_map(&tmDS, ds, dims, str, box) && tc::encode_map(&tmPD, pd, dims, str, box),
+                "relpos_attn_bwd: dS / Pd tensor map");
   }
   Params p;
   memset(&p, 0, sizeof(p));
@@ -772,9 +872,9 @@ extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t
   p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
   p.site = site;
   const int nc = dk / 64;
-  const int smem = 1024 + 2 * nc * 16384 + 4 * nc * 8192 + 16384 + NUM_SM_WARPS * 16 * 80 + 1024 + 128;
+  const int smem = 1024 + 2 * nc * 16384 + 3 * nc * 8192 + 2 * 16384 + 8 * 16 * 88 * 2 + 256 + 256;
   const int grid = B * H * ((S + BM - 1) / BM);
-  void* args[4] = {&tmQ, &tmDO, &tmDS, &p};
+  void* args[6] = {&tmQ, &tmDO, &tmBD, &tmDS, &tmPD, &p};
   const void* fn = dk == 192 ? (const void*)attn_bwd_kernel<192> : dk == 128 ? (const void*)attn_bwd_kernel<128> : (const void*)attn_bwd_kernel<64>;
   static bool attr[3] = {false, false, false};
   if (!attr[nc - 1]) {
@@ -783,5 +883,5 @@ extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t
     if (rc) return rc;
     attr[nc - 1] = true;
   }
-  return launch(fn, grid, smem, (cudaStream_t)stream, args, "relpos_attn_bwd");
+  return launch(fn, grid, NUM_THREADS_BWD, smem, (cudaStream_t)stream, args, "relpos_attn_bwd");
 }

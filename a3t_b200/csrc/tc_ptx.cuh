@@ -185,7 +185,7 @@ static inline EncodeTiledFn get_encode() {
 
 // 4-D tensor map (bf16, or fp32 when esize == 4): dims[0] contiguous; strides in elements for dims 1..3
 static inline bool encode_map(CUtensorMap* map, const void* base, const int64_t dims[4], const int64_t strides[3],
-                       const int box[4], int esize = 2) {
+                       const int box[4], int esize = 2, bool swizzle128 = true) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gd[4], gs[3];
@@ -196,7 +196,8 @@ static inline bool encode_map(CUtensorMap* map, const void* base, const int64_t 
   }
   for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides[i] * esize;
   CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
