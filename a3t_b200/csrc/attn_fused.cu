@@ -27,9 +27,13 @@ namespace fa {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int NUM_SM_WARPS = 8;                       // softmax warps: (warp & 3) = TMEM lane quarter, (warp >> 2) = column half
-constexpr int PRODUCER_WARP = 8, MMA_WARP = 9;
-constexpr int NUM_THREADS = 32 * (NUM_SM_WARPS + 2);
+constexpr int NUM_SM_WARPS = 16;   // softmax warps: (warp & 3) = TMEM lane quarter, (warp >> 2) = column quarter
+// three independent TMA producers (K, V, bias): each chain waits only on its own consumer, so a load is issued the
+// moment its buffer is free instead of queueing behind the other operands' waits
+constexpr int PRODUCER_WARP = NUM_SM_WARPS, V_WARP = NUM_SM_WARPS + 1, BIAS_WARP = NUM_SM_WARPS + 2, MMA_WARP = NUM_SM_WARPS + 3;
+constexpr int NUM_THREADS = 32 * (NUM_SM_WARPS + 4);
+constexpr int STORE_WARP = NUM_SM_WARPS + 4;   // backward only: TMA tensor stores of dS / Pd
+constexpr int NUM_THREADS_BWD = NUM_THREADS + 32;
 constexpr int SMEM_MAX = 227 * 1024;
 
 struct Params {
@@ -42,12 +46,20 @@ struct Params {
   __nv_bfloat16* dq;            // bwd out: dqkv4 base (B,S,4D); d(q+u) goes to columns [h*dk, (h+1)*dk)
   __nv_bfloat16* pd;            // bwd out: (B,H,S,ld) dropped probabilities
   __nv_bfloat16* dbd;           // bwd out: (B,H,S,ld) dBD_raw
+  long long* trace;             // tuning builds: per-role clock64 stamps of CTA 0 (NULL = off)
   int64_t ld;                   // row pitch of every (B,H,S,S) tensor, elements
   int B, H, S, D;
   float scale, c2;              // 1/sqrt(dk); scale * log2(e)
   float drop_p;
   uint32_t site;
 };
+
+#ifdef A3T_TUNING
+#define A3T_TRACE(role, idx) \
+  do { if (p.trace && blockIdx.x == 0 && (idx) < 256) p.trace[(role) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define A3T_TRACE(role, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -64,23 +76,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// rel_shift source of key j for query i inside one (b,h) block of BD_raw (pitch ld); -1: the structural zero / outside
-__device__ __forceinline__ int64_t shift_src(int i, int j, int S, int64_t ld) {
-  if (i >= S || j >= S || j == i + 1) return -1;
-  return j <= i ? (int64_t)i * ld + (S - 1 - i) + j : (int64_t)(i + 1) * ld - (i + 2) + j;
-}
-
-// validity bits of all keys of utterance b into shared memory (word w, bit e = key 32 w + e is a real key)
-__device__ __forceinline__ void build_key_bits(const uint8_t* __restrict__ km, int S, uint32_t sKB, int tid, int nthreads) {
+// validity bits of all keys of utterance b into shared memory (word w, bit e = key 32 w + e is a real key); one
+// coalesced byte load + ballot per word, words dealt round-robin to the calling warps
+__device__ __forceinline__ void build_key_bits(const uint8_t* __restrict__ km, int S, uint32_t sKB, int warp, int lane, int nwarps) {
   const int nwords = (S + 31) / 32 + 4;   // tiles read up to 128 keys past the last valid one
-  for (int w = tid; w < nwords; w += nthreads) {
-    uint32_t bits = 0;
-#pragma unroll 4
-    for (int e = 0; e < 32; e++) {
-      const int j = 32 * w + e;
-      if (j < S && km[j] != 0) bits |= 1u << e;
-    }
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sKB + 4 * w), "r"(bits) : "memory");
+  for (int w = warp; w < nwords; w += nwarps) {
+    const int j = 32 * w + lane;
+    const uint32_t bits = __ballot_sync(0xffffffffu, j < S && km[j] != 0);
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sKB + 4 * w), "r"(bits) : "memory");
   }
 }
 
@@ -104,29 +107,42 @@ __device__ __forceinline__ void drop_words(const Drop& dr, unsigned long long id
 // BD_raw: the band a tile needs is a parallelogram (one element of skew per query), and TMA wants the first column
 // of a box 16-byte aligned, so the box starts `sft` (0..7) elements early: row r holds the COLS values of its query
 // from element (15 - r + sft) on.  Thread = query reads its window as aligned words and re-aligns it with a funnel
-// shift: word k of the result = elements (2k, 2k+1) of the thread's column half.
+// shift: word k of the result = elements (2k, 2k+1) of the thread's column slice.
 __device__ __forceinline__ int box_col0(int S, int i_first, int j0, bool upper) {
   // first column query (i_first + 15) needs: rel_shift reads BD_raw[i, S-1-i+j] below the diagonal (j <= i) and
   // BD_raw[i+1, j-i-2] above it (j >= i+2; the box is then anchored one row lower)
   return upper ? j0 - (i_first + 15) - 2 : S - 1 - (i_first + 15) + j0;
 }
-template <int COLS, int HCOLS>   // COLS: keys per tile; HCOLS: keys per thread (column half)
-__device__ __forceinline__ void read_bias_window(uint32_t boxes, int sft, int lane, int hh, uint32_t (&out)[HCOLS / 2]) {
+template <int COLS, int TCOLS>   // COLS: keys per tile; TCOLS: keys per thread (column slice cs of the tile)
+__device__ __forceinline__ void read_bias_window(uint32_t boxes, int sft, int lane, int cs, uint32_t (&out)[TCOLS / 2]) {
   constexpr int PITCH = (COLS + 24) * 2;
   const int r = lane & 15;
-  const int e0 = 15 - r + sft + HCOLS * hh;
+  const int e0 = 15 - r + sft + TCOLS * cs;
   const uint32_t a = boxes + (lane >> 4) * (16 * PITCH) + r * PITCH + 4 * (e0 >> 1);
   const uint32_t sh = (uint32_t)(e0 & 1) * 16u;
-  uint32_t w[HCOLS / 2 + 1];
+  uint32_t w[TCOLS / 2 + 1];
 #pragma unroll
-  for (int k = 0; k <= HCOLS / 2; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(a + 4 * k) : "memory");
+  for (int k = 0; k <= TCOLS / 2; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[k]) : "r"(a + 4 * k) : "memory");
 #pragma unroll
-  for (int k = 0; k < HCOLS / 2; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
+  for (int k = 0; k < TCOLS / 2; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
+}
+// diagonal tile: keys j <= i take the lower band, j >= i + 2 the upper one, j == i + 1 is rel_shift's structural zero
+template <int N>
+__device__ __forceinline__ void merge_diag(uint32_t (&bw)[N], const uint32_t (&up)[N], int i, int j0) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int ja = j0 + 2 * k, jb = ja + 1;
+    const uint32_t lo16 = ja <= i ? (bw[k] & 0xFFFFu) : (ja == i + 1 ? 0u : (up[k] & 0xFFFFu));
+    const uint32_t hi16 = jb <= i ? (bw[k] & 0xFFFF0000u) : (jb == i + 1 ? 0u : (up[k] & 0xFFFF0000u));
+    bw[k] = lo16 | hi16;
+  }
 }
 
 // ================================================================================================
 // forward
 // ================================================================================================
+// Softmax warp (q, cq): q = warp & 3 is the TMEM lane quarter (hardware rule: warp w reads lanes 32 (w % 4) ...),
+// cq = warp >> 2 the column quarter; thread = one query row x 32 keys of the 128-key tile.
 template <int DK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBD,
@@ -135,10 +151,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   constexpr int NC = DK / 64;                  // 64-wide chunks of the head dimension
   constexpr uint32_t QB = NC * 16384u;         // one 128 x DK bf16 operand tile
   constexpr uint32_t BOX = 16 * 152 * 2;       // bias box of one 16-query group (128 keys + 15 of skew + 7 of alignment)
-  constexpr int HALF = DK / 2;                 // O columns per thread
+  constexpr int QCOLS = DK / 4;                // O columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + QB, sV = sK + QB, sP = sV + QB, sB = sP + 32768u, sRed = sB + 8 * BOX, sKB = sRed + 2048u,
+  const uint32_t sQ = base, sK = sQ + QB, sV = sK + QB, sP = sV + QB, sB = sP + 32768u, sRed = sB + 8 * BOX, sKB = sRed + 4096u,
                  sBar = sKB + 1024u;
   const uint32_t q_full = sBar, k_full = sBar + 8, k_empty = sBar + 16, v_full = sBar + 24, v_empty = sBar + 32,
                  p_full = sBar + 72, p_empty = sBar + 80, o_full = sBar + 88, tmem_slot = sBar + 96, b_full = sBar + 104,
@@ -179,6 +195,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_expect_tx(q_full, QB);
       for (int c = 0; c < NC; c++)
         for (int r = 0; r < 2; r++) tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
+      for (int t = 0; t < nkt; t++) {
+        const int j0 = t * 128;
+        if (t > 0) mbar_wait(k_empty, (t - 1) & 1);
+        mbar_expect_tx(k_full, QB);
+        for (int c = 0; c < NC; c++)
+          for (int r = 0; r < 2; r++)
+            tma_load_4d(sK + c * 16384 + r * 8192, &tmQKV, k_full, 2 * D + h * DK + 64 * c, j0 + 64 * r, b, 0);
+        A3T_TRACE(1, t);
+      }
+    }
+  } else if (warp == V_WARP) {
+    if (elect_one()) {
+      for (int t = 0; t < nkt; t++) {
+        const int j0 = t * 128;
+        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
+        mbar_expect_tx(v_full, QB);
+        for (int kc = 0; kc < 2; kc++)   // V as the MN-major B operand of P V: per 64-key chunk, NC atoms of 64 head columns
+          for (int a = 0; a < NC; a++)
+            tma_load_4d(sV + kc * (NC * 8192) + a * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * a, j0 + 64 * kc, b, 0);
+        A3T_TRACE(2, t);
+      }
+    }
+  } else if (warp == BIAS_WARP) {
+    if (elect_one()) {
       int nb = 0;   // bias loads issued
       auto load_bias = [&](int j0, bool upper) {
         if (nb > 0) mbar_wait(b_empty, (nb - 1) & 1);
@@ -187,22 +227,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const int i_first = i0 + 16 * g;
           tma_load_4d(sB + g * BOX, &tmBD, b_full, box_col0(S, i_first, j0, upper) & ~7, i_first + (upper ? 1 : 0), h, b);
         }
+        A3T_TRACE(3, nb);
         nb++;
       };
       for (int t = 0; t < nkt; t++) {
-        const int j0 = t * 128;
-        if (t > 0) mbar_wait(k_empty, (t - 1) & 1);
-        mbar_expect_tx(k_full, QB);
-        for (int c = 0; c < NC; c++)
-          for (int r = 0; r < 2; r++)
-            tma_load_4d(sK + c * 16384 + r * 8192, &tmQKV, k_full, 2 * D + h * DK + 64 * c, j0 + 64 * r, b, 0);
-        load_bias(j0, t > qt);          // t < qt: below the diagonal; t == qt: the lower part first
-        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
-        mbar_expect_tx(v_full, QB);
-        for (int kc = 0; kc < 2; kc++)   // V as the MN-major B operand of P V: per 64-key chunk, NC atoms of 64 head columns
-          for (int a = 0; a < NC; a++)
-            tma_load_4d(sV + kc * (NC * 8192) + a * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * a, j0 + 64 * kc, b, 0);
-        if (t == qt) load_bias(j0, true);   // the diagonal tile also needs the part above the diagonal
+        load_bias(t * 128, t > qt);              // t < qt: below the diagonal; t == qt: the lower part first
+        if (t == qt) load_bias(t * 128, true);   // the diagonal tile also needs the part above the diagonal
       }
     }
   } else if (warp == MMA_WARP) {
@@ -225,6 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                       (c | k) ? 1u : 0u);
         umma_commit(k_empty);
         umma_commit(s_full(t & 1));
+        A3T_TRACE(4, t);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -241,157 +272,195 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                       idesc_o, (t | kc | k) ? 1u : 0u);
         umma_commit(v_empty);
         umma_commit(p_empty);
+        A3T_TRACE(5, t);
       }
       umma_commit(o_full);
     }
   } else {
     // ===================================== softmax warps ====================================
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;
     const int row = q * 32 + lane, i = i0 + row;
+    const bool tr = warp == 0 && lane == 0;
     const uint8_t* km = p.keymask + (int64_t)b * S;
-    build_key_bits(km, S, sKB, threadIdx.x, NUM_SM_WARPS * 32);
+    build_key_bits(km, S, sKB, warp, lane, NUM_SM_WARPS);
     named_bar(5, NUM_SM_WARPS * 32);
     const Drop dr = make_drop(p.drop_p, p.seed, p.site);
     const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
     const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
+    // running maximum m in RAW score units (before the 1/sqrt(dk) scale); l accumulates exp2((x - m) c2) * inv_keep:
+    // the dropout scale is folded into the exponent, so kept probabilities need no multiply
     float m = -INFINITY, l = 0.f;
     const float c2 = p.c2;
+    const float lk = dr.on ? log2f(dr.inv_keep) : 0.f;
+    const float thr_raw = 8.f / c2;
     int nb = 0;   // bias boxes consumed
-    auto take_bias = [&](uint32_t (&w)[32], int jt, bool upper) {
+    auto take_bias = [&](uint32_t (&w)[16], int jt, bool upper) {
       mbar_wait(b_full, nb & 1);
-      read_bias_window<128, 64>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, hh, w);
+      read_bias_window<128, 32>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, cq, w);
       __syncwarp();
       if (lane == 0) mbar_arrive(b_empty);
       nb++;
     };
     for (int t = 0; t < nkt; t++) {
-      const int j0 = t * 128 + 64 * hh;
-      uint32_t bw[32], kb[2];
+      const int j0 = t * 128 + 32 * cq;
+      uint32_t bw[16], kb;
+      if (tr) A3T_TRACE(0, 8 * t);
       take_bias(bw, t * 128, t > qt);
-      if (t == qt) {   // diagonal tile: keys j <= i from the lower band, j >= i + 2 from the upper one, j == i + 1 is the zero
-        uint32_t up[32];
+      if (t == qt) {
+        uint32_t up[16];
         take_bias(up, t * 128, true);
-#pragma unroll
-        for (int k = 0; k < 32; k++) {
-          const int ja = j0 + 2 * k, jb = ja + 1;
-          const uint32_t lo16 = ja <= i ? (bw[k] & 0xFFFFu) : (ja == i + 1 ? 0u : (up[k] & 0xFFFFu));
-          const uint32_t hi16 = jb <= i ? (bw[k] & 0xFFFF0000u) : (jb == i + 1 ? 0u : (up[k] & 0xFFFF0000u));
-          bw[k] = lo16 | hi16;
-        }
+        merge_diag<16>(bw, up, i, j0);
       } else if (j0 == i + 1) {   // first key of the tile right of the diagonal, last query of the tile
         bw[0] &= 0xFFFF0000u;
       }
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(kb[0]), "=r"(kb[1]) : "r"(sKB + (uint32_t)(j0 >> 5) * 4u) : "memory");
+      if (tr) A3T_TRACE(0, 8 * t + 1);
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kb) : "r"(sKB + (uint32_t)(j0 >> 5) * 4u) : "memory");
       mbar_wait(s_full(t & 1), (t >> 1) & 1);
       tc_fence_after();
-      uint32_t s[64];
-      {
-        const uint32_t ta = tmem_base + 128u * (t & 1) + lane_t + 64u * hh;
-        tmem_ld32(ta, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tmem_ld32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld_wait();
-      }
+      if (tr) A3T_TRACE(0, 8 * t + 2);
+      uint32_t s[32];
+      tmem_ld32(tmem_base + 128u * (t & 1) + lane_t + 32u * cq, s);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(t & 1));
       float mx = -INFINITY;
+      if (kb == 0xFFFFFFFFu) {
 #pragma unroll
-      for (int c = 0; c < 64; c++) {
-        const float bias = (c & 1) ? bf_hi(bw[c >> 1]) : bf_lo(bw[c >> 1]);
-        float x = (__uint_as_float(s[c]) + bias) * c2;
-        x = ((kb[c >> 5] >> (c & 31)) & 1u) ? x : -INFINITY;
-        s[c] = __float_as_uint(x);
-        mx = fmaxf(mx, x);
+        for (int c = 0; c < 32; c++) {
+          const float x = __uint_as_float(s[c]) + ((c & 1) ? bf_hi(bw[c >> 1]) : bf_lo(bw[c >> 1]));
+          s[c] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+          float x = __uint_as_float(s[c]) + ((c & 1) ? bf_hi(bw[c >> 1]) : bf_lo(bw[c >> 1]));
+          x = ((kb >> c) & 1u) ? x : -INFINITY;
+          s[c] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
       }
-      // the two threads of a row (this warp and warp ^ 4) agree on the tile maximum
-      const uint32_t red = sRed + (uint32_t)(t & 1) * 1024u;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (hh * 128 + row) * 4), "f"(mx) : "memory");
-      named_bar(1 + q, 64);
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(red + ((hh ^ 1) * 128 + row) * 4) : "memory");
-      const float m_new = fmaxf(m, fmaxf(mx, other));
+      // the four threads of a row (warps q, q+4, q+8, q+12) agree on the tile maximum
+      const uint32_t red = sRed + (uint32_t)(t & 1) * 2048u + row * 4;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + cq * 512), "f"(mx) : "memory");
+      named_bar(1 + q, 128);
+      if (tr) A3T_TRACE(0, 8 * t + 3);
+      float m_new = m;
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(red + o * 512) : "memory");
+        m_new = fmaxf(m_new, other);
+      }
       // lazy rescale: the running maximum only moves when it grows by more than 2^8 (P stays <= 256: exact enough in
       // bf16 / fp32 and the accumulator in TMEM is rarely touched)
-      const bool resc = m_new > m + 8.f;
+      const bool resc = m_new > m + thr_raw;
       float fac = 1.f;
       if (resc) {
-        fac = ex2(m - m_new);   // m = -inf on the first tile: 0
+        fac = ex2((m - m_new) * c2);   // m = -inf on the first tile: 0
         l *= fac;
         m = m_new;
       }
-      const float m_use = (m == -INFINITY) ? 0.f : m;
-      uint32_t rw[32];
-      if (dr.on) drop_words<64>(dr, drow + (unsigned long long)j0, rw);
-      uint32_t pk[32];
+      const float off = lk - ((m == -INFINITY) ? 0.f : m) * c2;
+      uint32_t rw[16];
+      if (dr.on) drop_words<32>(dr, drow + (unsigned long long)j0, rw);
+      uint32_t pk[16];
 #pragma unroll
-      for (int k = 0; k < 32; k++) {
-        float p0 = ex2(__uint_as_float(s[2 * k]) - m_use), p1 = ex2(__uint_as_float(s[2 * k + 1]) - m_use);
+      for (int k = 0; k < 16; k++) {
+        float p0 = ex2(fmaf(__uint_as_float(s[2 * k]), c2, off)), p1 = ex2(fmaf(__uint_as_float(s[2 * k + 1]), c2, off));
         l += p0 + p1;
         if (dr.on) {
-          p0 = ((rw[k] & 0xFFFFu) >= dr.thr) ? p0 * dr.inv_keep : 0.f;
-          p1 = ((rw[k] >> 16) >= dr.thr) ? p1 * dr.inv_keep : 0.f;
+          p0 = ((rw[k] & 0xFFFFu) >= dr.thr) ? p0 : 0.f;
+          p1 = ((rw[k] >> 16) >= dr.thr) ? p1 : 0.f;
         }
         pk[k] = pack_bf16(p0, p1);
       }
+      if (tr) A3T_TRACE(0, 8 * t + 4);
       if (t > 0) {
         mbar_wait(p_empty, (t - 1) & 1);   // P V of the previous tile has read the P buffer and updated O
         if (__any_sync(0xffffffffu, resc)) {
           tc_fence_after();
-#pragma unroll
-          for (int g = 0; g < HALF / 32; g++) {
+          const uint32_t ta = tmem_O + lane_t + (uint32_t)(cq * QCOLS);
+          if constexpr (QCOLS >= 32) {
             uint32_t o[32];
-            const uint32_t ta = tmem_O + lane_t + (uint32_t)(hh * HALF + g * 32);
             tmem_ld32(ta, o);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 32; c++) o[c] = __float_as_uint(__uint_as_float(o[c]) * fac);
             tmem_st32(ta, o);
           }
+          if constexpr (QCOLS % 32 == 16) {
+            uint32_t o[16];
+            tmem_ld16(ta + (QCOLS - 16), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; c++) o[c] = __float_as_uint(__uint_as_float(o[c]) * fac);
+            tmem_st16(ta + (QCOLS - 16), o);
+          }
           tmem_st_wait();
           tc_fence_before();
         }
       }
-      const uint32_t prow = sP + hh * 16384 + row * 128;
+      if (tr) A3T_TRACE(0, 8 * t + 5);
+      // 32 keys = 64 bytes = chunks 4 (cq & 1) .. +3 of the row in the K-major operand tile of keys 64 (cq >> 1) ..
+      const uint32_t prow = sP + (cq >> 1) * 16384 + row * 128;
       const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-      for (int u = 0; u < 8; u++)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((u ^ sw) << 4)), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
-                     "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+      for (int u = 0; u < 4; u++)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((4 * (cq & 1) + u) ^ sw) << 4)), "r"(pk[4 * u]),
+                     "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
                      : "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tr) A3T_TRACE(0, 8 * t + 6);
     }
     // ---- epilogue: ctx = O / l, lse ----
-    const uint32_t red = sRed + (uint32_t)(nkt & 1) * 1024u;
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (hh * 128 + row) * 4), "f"(l) : "memory");
-    named_bar(1 + q, 64);
-    float lo;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(red + ((hh ^ 1) * 128 + row) * 4) : "memory");
-    const float ltot = l + lo;
-    const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
+    const uint32_t red = sRed + (uint32_t)(nkt & 1) * 2048u + row * 4;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + cq * 512), "f"(l) : "memory");
+    named_bar(1 + q, 128);
+    float ltot = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(red + o * 512) : "memory");
+      ltot += other;
+    }
+    // ltot carries the folded dropout scale: sum of probabilities = ltot / inv_keep
+    const float inv = ltot > 0.f ? dr.inv_keep / ltot : 0.f;
     mbar_wait(o_full, 0);
     tc_fence_after();
-    __nv_bfloat16* crow = p.ctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF;
-#pragma unroll
-    for (int g = 0; g < HALF / 32; g++) {
+    __nv_bfloat16* crow = p.ctx + ((int64_t)b * S + i) * D + h * DK + cq * QCOLS;
+    const uint32_t ta = tmem_O + lane_t + (uint32_t)(cq * QCOLS);
+    auto store8 = [&](const uint32_t* o, int col) {
+      uint4 v;
+      v.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      v.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      v.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      v.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      *reinterpret_cast<uint4*>(crow + col) = v;
+    };
+    if constexpr (QCOLS >= 32) {
       uint32_t o[32];
-      tmem_ld32(tmem_O + lane_t + (uint32_t)(hh * HALF + g * 32), o);
+      tmem_ld32(ta, o);
       tmem_ld_wait();
       if (i < S) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * u]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
-          v.y = pack_bf16(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
-          v.z = pack_bf16(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
-          v.w = pack_bf16(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
-          *reinterpret_cast<uint4*>(crow + g * 32 + 8 * u) = v;
-        }
+        for (int u = 0; u < 4; u++) store8(&o[8 * u], 8 * u);
       }
     }
-    if (hh == 0 && i < S) p.lse[(int64_t)bh * S + i] = ltot > 0.f ? m + log2f(ltot) : 1e30f;
+    if constexpr (QCOLS % 32 == 16) {
+      uint32_t o[16];
+      tmem_ld16(ta + (QCOLS - 16), o);
+      tmem_ld_wait();
+      if (i < S) {
+        store8(&o[0], QCOLS - 16);
+        store8(&o[8], QCOLS - 8);
+      }
+    }
+    if (cq == 0 && i < S) p.lse[(int64_t)bh * S + i] = ltot > 0.f ? m * c2 + log2f(ltot) - lk : 1e30f;
   }
 
   tc_fence_before();
@@ -407,10 +476,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // ================================================================================================
 // 64-key tiles.  Shared memory: Qu and dO resident (2 x 128 x DK), K double buffered and V single buffered (3 x 64 x DK),
 // the dS operand tile and the Pd staging tile (2 x 128 x 64), the bias boxes.  TMEM: S and dP double buffered
-// (4 x 64 columns), dQu (DK).  Warp 10 issues the TMA tensor stores of dS and Pd.
-constexpr int STORE_WARP = 10;
-constexpr int NUM_THREADS_BWD = NUM_THREADS + 32;
-
+// (4 x 64 columns), dQu (DK).  STORE_WARP issues the TMA tensor stores of dS and Pd.  Softmax warp (q, cq): one query
+// row x 16 keys per thread.
 template <int DK>
 __global__ void __launch_bounds__(NUM_THREADS_BWD, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -421,7 +488,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   constexpr uint32_t QB = NC * 16384u;         // 128 x DK
   constexpr uint32_t KB = NC * 8192u;          // 64 x DK
   constexpr uint32_t BOX = 16 * 88 * 2;        // bias box of one 16-query group (64 keys + 15 of skew + 7 of alignment)
-  constexpr int HALF = DK / 2;
+  constexpr int QCOLS = DK / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sDO = sQ + QB, sK = sDO + QB, sV = sK + 2 * KB, sDS = sV + KB, sPD = sDS + 16384u, sB = sPD + 16384u,
@@ -477,6 +544,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tma_load_4d(sQ + c * 16384 + r * 8192, &tmQKV, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
           tma_load_4d(sDO + c * 16384 + r * 8192, &tmDO, q_full, h * DK + 64 * c, i0 + 64 * r, b, 0);
         }
+      for (int t = 0; t < nkt; t++) {
+        const int st = t & 1, j0 = t * 64;
+        if (t >= 2) mbar_wait(k_empty(st), ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(k_full(st), KB);
+        for (int c = 0; c < NC; c++) tma_load_4d(sK + st * KB + c * 8192, &tmQKV, k_full(st), 2 * D + h * DK + 64 * c, j0, b, 0);
+        A3T_TRACE(1, t);
+      }
+    }
+  } else if (warp == V_WARP) {
+    if (elect_one()) {
+      for (int t = 0; t < nkt; t++) {
+        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
+        mbar_expect_tx(v_full, KB);
+        for (int c = 0; c < NC; c++) tma_load_4d(sV + c * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * c, t * 64, b, 0);
+        A3T_TRACE(2, t);
+      }
+    }
+  } else if (warp == BIAS_WARP) {
+    if (elect_one()) {
       int nb = 0;
       auto load_bias = [&](int j0, bool upper) {
         if (nb > 0) mbar_wait(b_empty, (nb - 1) & 1);
@@ -485,18 +571,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const int i_first = i0 + 16 * g;
           tma_load_4d(sB + g * BOX, &tmBD, b_full, box_col0(S, i_first, j0, upper) & ~7, i_first + (upper ? 1 : 0), h, b);
         }
+        A3T_TRACE(3, nb);
         nb++;
       };
       for (int t = 0; t < nkt; t++) {
-        const int st = t & 1, j0 = t * 64;
-        if (t >= 2) mbar_wait(k_empty(st), ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(k_full(st), KB);
-        for (int c = 0; c < NC; c++) tma_load_4d(sK + st * KB + c * 8192, &tmQKV, k_full(st), 2 * D + h * DK + 64 * c, j0, b, 0);
-        load_bias(j0, (t >> 1) > qt);
-        if (t > 0) mbar_wait(v_empty, (t - 1) & 1);
-        mbar_expect_tx(v_full, KB);
-        for (int c = 0; c < NC; c++) tma_load_4d(sV + c * 8192, &tmQKV, v_full, 3 * D + h * DK + 64 * c, j0, b, 0);
-        if (is_diag(t)) load_bias(j0, true);
+        load_bias(t * 64, (t >> 1) > qt);
+        if (is_diag(t)) load_bias(t * 64, true);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -528,6 +608,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                       dV + (uint64_t)((c * 8192 + k * 32) >> 4), idesc_s, (c | k) ? 1u : 0u);
         umma_commit(v_empty);
         umma_commit(s_full(st));
+        A3T_TRACE(4, t);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -542,6 +623,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_bf16(tmem_dQ, dDS + (uint64_t)((k * 32) >> 4), dKm + (uint64_t)((k * 2048) >> 4), idesc_q, (t | k) ? 1u : 0u);
         umma_commit(k_empty(t & 1));
         umma_commit(out_empty);
+        A3T_TRACE(5, t);
       }
       umma_commit(o_full);
     }
@@ -559,143 +641,150 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(out_empty);
+        A3T_TRACE(6, t);
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;
     const int row = q * 32 + lane, i = i0 + row;
     const bool row_ok = i < S;
+    const bool tr = warp == 0 && lane == 0;
     const int ld = (int)p.ld;
     const int64_t blk = (int64_t)bh * S * p.ld;
     unsigned short* const dbd = reinterpret_cast<unsigned short*>(p.dbd + blk);
     const uint8_t* km = p.keymask + (int64_t)b * S;
-    build_key_bits(km, S, sKB, threadIdx.x, NUM_SM_WARPS * 32);
+    build_key_bits(km, S, sKB, warp, lane, NUM_SM_WARPS);
     const Drop dr = make_drop(p.drop_p, p.seed, p.site);
     const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
     const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
-    const float c2 = p.c2, scale = p.scale;
+    const float c2 = p.c2;
     // rows of dBD_raw nobody's rel_shift reads: BD_raw[0, 0 .. S-2] (the row the reshape drops)
     if (qt == 0)
       for (int j = threadIdx.x; j < S - 1; j += NUM_SM_WARPS * 32) dbd[j] = 0;
-    // delta_i = sum_c dO[i,c] O[i,c] over the head: each of the row's two threads takes half of the columns
+    // delta_i = sum_c dO[i,c] O[i,c] over the head: each of the row's four threads takes a quarter of the columns
     float delta = 0.f;
     if (row_ok) {
-      const uint4* a = reinterpret_cast<const uint4*>(p.dctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF);
-      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((int64_t)b * S + i) * D + h * DK + hh * HALF);
+      const uint4* a = reinterpret_cast<const uint4*>(p.dctx + ((int64_t)b * S + i) * D + h * DK + cq * QCOLS);
+      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((int64_t)b * S + i) * D + h * DK + cq * QCOLS);
 #pragma unroll
-      for (int u = 0; u < HALF / 8; u++) {
+      for (int u = 0; u < QCOLS / 8; u++) {
         const uint4 x = __ldg(a + u), y = __ldg(o + u);
         delta += bf_lo(x.x) * bf_lo(y.x) + bf_hi(x.x) * bf_hi(y.x) + bf_lo(x.y) * bf_lo(y.y) + bf_hi(x.y) * bf_hi(y.y) +
                  bf_lo(x.z) * bf_lo(y.z) + bf_hi(x.z) * bf_hi(y.z) + bf_lo(x.w) * bf_lo(y.w) + bf_hi(x.w) * bf_hi(y.w);
       }
     }
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + (hh * 128 + row) * 4), "f"(delta) : "memory");
-    named_bar(5, NUM_SM_WARPS * 32);   // key bits and the delta halves are visible
-    {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + (cq * 128 + row) * 4), "f"(delta) : "memory");
+    named_bar(5, NUM_SM_WARPS * 32);   // key bits and the delta quarters are visible
+    delta = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
       float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(sRed + ((hh ^ 1) * 128 + row) * 4) : "memory");
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(sRed + (o * 128 + row) * 4) : "memory");
       delta += other;
     }
     named_bar(5, NUM_SM_WARPS * 32);   // (the exchange area is the dS staging tile: everyone has read before anyone writes)
     const float lse = row_ok ? p.lse[(int64_t)bh * S + i] : 1e30f;
-    // scatter geometry of this warp's 32 queries (rel_shift^T): element (ii, j) -> dBD_raw offset arow + j (+ dl above the diagonal)
+    // dS = P (dropout'(dP) - delta) scale with the scales folded: dS = P * fma(dP, ks, -ds) (kept) or P * (-ds) (dropped)
+    const float ks = dr.inv_keep * p.scale, dsn = -delta * p.scale;
+    // scatter geometry (rel_shift^T): element (ii, j) -> dBD_raw offset ii (ld - 1) + S - 1 + j (+ dl above the diagonal)
     const int dl = ld - S - 1;
-    const uint32_t tbuf = sPD + q * 4096 + hh * 2048;   // transposition scratch inside this warp pair's rows of the Pd staging tile
+    const uint32_t tbuf = sPD + q * 4096 + cq * 1024;   // scratch inside this warp quartet's rows of the Pd staging tile
     int nb = 0;
-    auto take_bias = [&](uint32_t (&w)[16], int jt, bool upper) {
+    auto take_bias = [&](uint32_t (&w)[8], int jt, bool upper) {
       mbar_wait(b_full, nb & 1);
-      read_bias_window<64, 32>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, hh, w);
+      read_bias_window<64, 16>(sB + 2 * q * BOX, box_col0(S, i0, jt, upper) & 7, lane, cq, w);
       __syncwarp();
       if (lane == 0) mbar_arrive(b_empty);
       nb++;
     };
     for (int t = 0; t < nkt; t++) {
       const int st = t & 1;
-      const int j0 = t * 64 + 32 * hh;
-      uint32_t bw[16], kb;
+      const int j0 = t * 64 + 16 * cq;
+      uint32_t bw[8], kb;
+      if (tr) A3T_TRACE(0, 8 * t);
       take_bias(bw, t * 64, (t >> 1) > qt);
       if (is_diag(t)) {
-        uint32_t up[16];
+        uint32_t up[8];
         take_bias(up, t * 64, true);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          const int ja = j0 + 2 * k, jb = ja + 1;
-          const uint32_t lo16 = ja <= i ? (bw[k] & 0xFFFFu) : (ja == i + 1 ? 0u : (up[k] & 0xFFFFu));
-          const uint32_t hi16 = jb <= i ? (bw[k] & 0xFFFF0000u) : (jb == i + 1 ? 0u : (up[k] & 0xFFFF0000u));
-          bw[k] = lo16 | hi16;
-        }
+        merge_diag<8>(bw, up, i, j0);
       } else if (j0 == i + 1) {
         bw[0] &= 0xFFFF0000u;
       }
+      if (tr) A3T_TRACE(0, 8 * t + 1);
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kb) : "r"(sKB + (uint32_t)(j0 >> 5) * 4u) : "memory");
+      kb = (kb >> (j0 & 31)) & 0xFFFFu;
       mbar_wait(s_full(st), (t >> 1) & 1);
       tc_fence_after();
-      uint32_t s[32], dp[32];
-      tmem_ld32(tmem_base + 64u * st + lane_t + 32u * hh, s);
-      tmem_ld32(tmem_base + 128u + 64u * st + lane_t + 32u * hh, dp);
+      if (tr) A3T_TRACE(0, 8 * t + 2);
+      uint32_t s[16], dp[16];
+      tmem_ld16(tmem_base + 64u * st + lane_t + 16u * cq, s);
+      tmem_ld16(tmem_base + 128u + 64u * st + lane_t + 16u * cq, dp);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(st));
-      uint32_t rw[16];
-      if (dr.on) drop_words<32>(dr, drow + (unsigned long long)j0, rw);
-      uint32_t pdw[16], dsw[16];
+      uint32_t rw[8];
+      if (dr.on) drop_words<16>(dr, drow + (unsigned long long)j0, rw);
+      uint32_t pdw[8], dsw[8];
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
+      for (int k = 0; k < 8; k++) {
         float pv[2], dv[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int c = 2 * k + e;
-          const float bias = e ? bf_hi(bw[k]) : bf_lo(bw[k]);
-          const float x = (__uint_as_float(s[c]) + bias) * c2;
+          const float x = __uint_as_float(s[c]) + (e ? bf_hi(bw[k]) : bf_lo(bw[k]));
           const bool valid = ((kb >> c) & 1u) != 0;
-          const float P = valid ? ex2(x - lse) : 0.f;
-          float g = __uint_as_float(dp[c]);
-          float Pd = P;
-          if (dr.on) {
-            const bool keep = (e ? (rw[k] >> 16) : (rw[k] & 0xFFFFu)) >= dr.thr;
-            Pd = keep ? P * dr.inv_keep : 0.f;
-            g = keep ? g * dr.inv_keep : 0.f;
-          }
-          pv[e] = Pd;
-          dv[e] = P * (g - delta) * scale;
+          const float P = valid ? ex2(fmaf(x, c2, -lse)) : 0.f;
+          const float g = __uint_as_float(dp[c]);
+          bool keep = true;
+          if (dr.on) keep = (e ? (rw[k] >> 16) : (rw[k] & 0xFFFFu)) >= dr.thr;
+          pv[e] = keep ? (dr.on ? P * dr.inv_keep : P) : 0.f;
+          dv[e] = P * (keep ? fmaf(g, ks, dsn) : dsn);
         }
         pdw[k] = pack_bf16(pv[0], pv[1]);
         dsw[k] = pack_bf16(dv[0], dv[1]);
       }
+      if (tr) A3T_TRACE(0, 8 * t + 3);
       // ---- outputs.  The staging tiles are free once the previous tile's dQu MMA and tensor stores have read them ----
       if (t > 0) mbar_wait(out_empty, (t - 1) & 1);
+      if (tr) A3T_TRACE(0, 8 * t + 4);
       // dBD_raw = rel_shift^T(dS): thread-per-query registers -> scratch -> lanes along the key axis, 2-byte stores
-      // (rows of dBD_raw shift by one element per query: no wider aligned store exists)
+      // (rows of dBD_raw shift by one element per query: no wider aligned store exists); two queries per instruction
+      {
+        const int c = lane & 15, rr = lane >> 4;
+        const int j = j0 + c;
+        const bool j_ok = j < S;
+        unsigned short* const pl = dbd + j;
 #pragma unroll
-      for (int half = 0; half < 2; half++) {        // 16 queries at a time
-        if ((lane >> 4) == half) {
+        for (int half = 0; half < 2; half++) {        // 16 queries at a time
+          if ((lane >> 4) == half) {
 #pragma unroll
-          for (int c = 0; c < 4; c++)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 80 + 16 * c), "r"(dsw[4 * c]),
-                         "r"(dsw[4 * c + 1]), "r"(dsw[4 * c + 2]), "r"(dsw[4 * c + 3])
-                         : "memory");
+            for (int u = 0; u < 2; u++)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 48 + 16 * u), "r"(dsw[4 * u]),
+                           "r"(dsw[4 * u + 1]), "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
+                           : "memory");
+          }
+          __syncwarp();
+          const int ii0 = i0 + q * 32 + half * 16 + rr;
+          int arow = ii0 * (ld - 1) + S - 1;      // offset of (ii, 0) through the lower band
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const int ii = ii0 + 2 * it;
+            unsigned short v;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + (2 * it + rr) * 48 + 2 * c) : "memory");
+            if (j_ok && ii < S && j != ii + 1) pl[arow + (j > ii ? dl : 0)] = v;
+            arow += 2 * (ld - 1);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        const int j = j0 + lane;
-        const int ii0 = i0 + q * 32 + half * 16;
-        int arow = ii0 * (ld - 1) + S - 1 + j;      // offset of (ii0, j) through the lower band
-#pragma unroll 8
-        for (int r = 0; r < 16; r++) {
-          const int ii = ii0 + r;
-          unsigned short v;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + r * 80 + 2 * lane) : "memory");
-          if (ii < S && j < S && j != ii + 1) dbd[arow + (j > ii ? dl : 0)] = v;
-          arow += ld - 1;
-        }
-        __syncwarp();
       }
-      named_bar(1 + q, 64);   // the partner warp's scratch lives in the same rows of the staging tile
+      named_bar(1 + q, 128);   // the other warps' scratch lives in the same rows of the staging tile
+      if (tr) A3T_TRACE(0, 8 * t + 5);
       const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t off = row * 128 + (((4 * hh + u) ^ sw) << 4);
+      for (int u = 0; u < 2; u++) {
+        const uint32_t off = row * 128 + (((2 * cq + u) ^ sw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dsw[4 * u]), "r"(dsw[4 * u + 1]),
                      "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
                      : "memory");
@@ -707,26 +796,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(out_full);
+      if (tr) A3T_TRACE(0, 8 * t + 6);
     }
     // ---- epilogue: d(q+u) -> dqkv4[:, :, h*dk ...] ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    __nv_bfloat16* qrow = p.dq + ((int64_t)b * S + i) * (4 * (int64_t)D) + h * DK + hh * HALF;
-#pragma unroll
-    for (int g = 0; g < HALF / 32; g++) {
+    __nv_bfloat16* qrow = p.dq + ((int64_t)b * S + i) * (4 * (int64_t)D) + h * DK + cq * QCOLS;
+    const uint32_t ta = tmem_dQ + lane_t + (uint32_t)(cq * QCOLS);
+    auto store8 = [&](const uint32_t* o, int col) {
+      uint4 v;
+      v.x = pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1]));
+      v.y = pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3]));
+      v.z = pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5]));
+      v.w = pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7]));
+      *reinterpret_cast<uint4*>(qrow + col) = v;
+    };
+    if constexpr (QCOLS >= 32) {
       uint32_t o[32];
-      tmem_ld32(tmem_dQ + lane_t + (uint32_t)(hh * HALF + g * 32), o);
+      tmem_ld32(ta, o);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * u]), __uint_as_float(o[8 * u + 1]));
-          v.y = pack_bf16(__uint_as_float(o[8 * u + 2]), __uint_as_float(o[8 * u + 3]));
-          v.z = pack_bf16(__uint_as_float(o[8 * u + 4]), __uint_as_float(o[8 * u + 5]));
-          v.w = pack_bf16(__uint_as_float(o[8 * u + 6]), __uint_as_float(o[8 * u + 7]));
-          *reinterpret_cast<uint4*>(qrow + g * 32 + 8 * u) = v;
-        }
+        for (int u = 0; u < 4; u++) store8(&o[8 * u], 8 * u);
+      }
+    }
+    if constexpr (QCOLS % 32 == 16) {
+      uint32_t o[16];
+      tmem_ld16(ta + (QCOLS - 16), o);
+      tmem_ld_wait();
+      if (row_ok) {
+        store8(&o[0], QCOLS - 16);
+        store8(&o[8], QCOLS - 8);
       }
     }
   }
@@ -789,6 +889,12 @@ static int launch(const void* fn, int grid, int threads, int smem, cudaStream_t 
 
 using namespace a3t;
 
+static long long* g_trace = nullptr;   // tuning builds only (a3t_attn_set_trace)
+extern "C" int a3t_attn_set_trace(void* device_buffer) {
+  g_trace = (long long*)device_buffer;
+  return A3T_OK;
+}
+
 extern "C" int a3t_attn_fused_supported(int B, int H, int S, int D) {
   if (B < 1 || H < 1 || S < 1 || D < 1 || D % H) return 0;
   const int dk = D / H;
@@ -825,9 +931,10 @@ extern "C" int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t
   p.bd_raw = (const __nv_bfloat16*)bd_raw; p.keymask = keymask; p.seed = seed; p.lse = lse; p.ctx = (__nv_bfloat16*)ctx;
   p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
   p.site = site;
+  p.trace = g_trace;
   const int nc = dk / 64;
   A3T_REQUIRE(S <= 8000, "relpos_attn_fwd: S=%d exceeds the key-bit table", S);
-  const int smem = 1024 + 3 * nc * 16384 + 32768 + 8 * 16 * 152 * 2 + 2048 + 1024 + 128;
+  const int smem = 1024 + 3 * nc * 16384 + 32768 + 8 * 16 * 152 * 2 + 4096 + 1024 + 128;
   const int grid = B * H * ((S + BM - 1) / BM);
   void* args[3] = {&tm, &tmBD, &p};
   const void* fn = dk == 192 ? (const void*)attn_fwd_kernel<192> : dk == 128 ? (const void*)attn_fwd_kernel<128> : (const void*)attn_fwd_kernel<64>;
@@ -871,6 +978,7 @@ extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t
   p.pd = (__nv_bfloat16*)pd; p.dbd = (__nv_bfloat16*)dbd;
   p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
   p.site = site;
+  p.trace = g_trace;
   const int nc = dk / 64;
   const int smem = 1024 + 2 * nc * 16384 + 3 * nc * 8192 + 2 * 16384 + 8 * 16 * 88 * 2 + 256 + 256;
   const int grid = B * H * ((S + BM - 1) / BM);
