@@ -78,8 +78,9 @@ _SIGS = {
     "a3t_relpos_softmax_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_relpos_softmax_bwd": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_attn_fused_supported": [_I, _I, _I, _I],
+    "a3t_attn_set_trace": [_P],
     "a3t_relpos_attn_fwd": [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
-    "a3t_relpos_attn_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
+    "a3t_relpos_attn_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _U, _P],
     "a3t_glu_dwconv_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "a3t_dwconv_bwd_blocks": [_I, _I],
     "a3t_glu_dwconv_bwd": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -527,8 +527,9 @@ class CudaBackend:
         pd, ds, dbd = self._like(bd), self._like(bd), self._like(bd)
         ld, sb1, sb2 = self._sstr(bd)
         pr, seed, site = self._drop(drop)
-        call("a3t_relpos_attn_bwd", _p(qkv4), _p(bd), ld, _p(_u8(keymask)), _p(ctx), _p(dctx), _p(lse), _p(dqkv4), _p(pd),
-             _p(ds), _p(dbd), Bn, H, S, D, scale, pr, seed, site, _stream(qkv4))
+        delta = torch.empty(Bn, H, S, dtype=torch.float32, device=dev)
+        call("a3t_relpos_attn_bwd", _p(qkv4), _p(bd), ld, _p(_u8(keymask)), _p(ctx), _p(dctx), _p(lse), _p(delta), _p(dqkv4),
+             _p(pd), _p(ds), _p(dbd), Bn, H, S, D, scale, pr, seed, site, _stream(qkv4))
         dts, dtq = _dt(ds), _dt(qkv4)
         a_row = dict(sa_m=ld, sa_k=1, sa_b1=sb1, sa_b2=sb2)   # A[i, j]
         a_col = dict(sa_m=1, sa_k=ld, sa_b1=sb1, sa_b2=sb2)   # A^T

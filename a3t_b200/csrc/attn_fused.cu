@@ -43,6 +43,7 @@ struct Params {
   float* lse;                   // (B,H,S) log2-domain log-sum-exp of the scaled scores
   __nv_bfloat16* ctx;           // fwd out / bwd in: (B,S,D)
   const __nv_bfloat16* dctx;    // bwd in: (B,S,D)
+  float* delta;                 // bwd workspace: (B,H,S) sum_c dO O per (row, head), written by attn_delta_kernel
   __nv_bfloat16* dq;            // bwd out: dqkv4 base (B,S,4D); d(q+u) goes to columns [h*dk, (h+1)*dk)
   __nv_bfloat16* pd;            // bwd out: (B,H,S,ld) dropped probabilities
   __nv_bfloat16* dbd;           // bwd out: (B,H,S,ld) dBD_raw
@@ -77,13 +78,21 @@ __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w <<
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // validity bits of all keys of utterance b into shared memory (word w, bit e = key 32 w + e is a real key); one
-// coalesced byte load + ballot per word, words dealt round-robin to the calling warps
+// coalesced byte load + ballot per word, words dealt round-robin to the calling warps, loads issued back to back
 __device__ __forceinline__ void build_key_bits(const uint8_t* __restrict__ km, int S, uint32_t sKB, int warp, int lane, int nwarps) {
   const int nwords = (S + 31) / 32 + 4;   // tiles read up to 128 keys past the last valid one
-  for (int w = warp; w < nwords; w += nwarps) {
-    const int j = 32 * w + lane;
-    const uint32_t bits = __ballot_sync(0xffffffffu, j < S && km[j] != 0);
-    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sKB + 4 * w), "r"(bits) : "memory");
+  for (int w0 = warp; w0 < nwords; w0 += 4 * nwarps) {
+    uint8_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = 32 * (w0 + u * nwarps) + lane;
+      v[u] = j < S ? km[j] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, v[u] != 0);
+      if (lane == 0 && w0 + u * nwarps < nwords) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sKB + 4 * (w0 + u * nwarps)), "r"(bits) : "memory");
+    }
   }
 }
 
@@ -512,7 +521,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmDO) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBD) : "memory");
-    mbar_init(q_full, 1); mbar_init(out_full, NUM_SM_WARPS); mbar_init(out_empty, 2); mbar_init(o_full, 1);
+    mbar_init(q_full, 1); mbar_init(out_full, NUM_SM_WARPS); mbar_init(out_empty, 2 + NUM_SM_WARPS); mbar_init(o_full, 1);
     mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(b_full, 1); mbar_init(b_empty, NUM_SM_WARPS);
     for (int i = 0; i < 2; i++) {
       mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(s_empty(i), NUM_SM_WARPS);
@@ -650,46 +659,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int row = q * 32 + lane, i = i0 + row;
     const bool row_ok = i < S;
     const bool tr = warp == 0 && lane == 0;
-    const int ld = (int)p.ld;
-    const int64_t blk = (int64_t)bh * S * p.ld;
-    unsigned short* const dbd = reinterpret_cast<unsigned short*>(p.dbd + blk);
     const uint8_t* km = p.keymask + (int64_t)b * S;
     build_key_bits(km, S, sKB, warp, lane, NUM_SM_WARPS);
+    // dBD_raw = rel_shift^T(dS) is written from the STAGED dS tile with lanes along the key axis (rows of dBD_raw shift
+    // by one element per query, so no aligned vector store exists: 2-byte elements, 64 contiguous bytes per row and
+    // instruction); this warp scatters query rows 8 warp .. +7 of every tile
+    const int ld = (int)p.ld;
+    unsigned short* const dbd = reinterpret_cast<unsigned short*>(p.dbd + (int64_t)bh * S * p.ld);
+    const int dl = ld - S - 1;                              // lower band -> upper band offset
+    if (qt == 0)                                            // BD_raw[0, 0 .. S-2]: the row the reshape drops, gradient 0
+      for (int j = threadIdx.x; j < S - 1; j += NUM_SM_WARPS * 32) dbd[j] = 0;
     const Drop dr = make_drop(p.drop_p, p.seed, p.site);
     const unsigned long long drow = ((unsigned long long)bh * S + (unsigned long long)min(i, S - 1)) * (unsigned long long)S;
     const uint32_t lane_t = ((uint32_t)(q * 32) << 16);
     const float c2 = p.c2;
-    // rows of dBD_raw nobody's rel_shift reads: BD_raw[0, 0 .. S-2] (the row the reshape drops)
-    if (qt == 0)
-      for (int j = threadIdx.x; j < S - 1; j += NUM_SM_WARPS * 32) dbd[j] = 0;
-    // delta_i = sum_c dO[i,c] O[i,c] over the head: each of the row's four threads takes a quarter of the columns
-    float delta = 0.f;
-    if (row_ok) {
-      const uint4* a = reinterpret_cast<const uint4*>(p.dctx + ((int64_t)b * S + i) * D + h * DK + cq * QCOLS);
-      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((int64_t)b * S + i) * D + h * DK + cq * QCOLS);
-#pragma unroll
-      for (int u = 0; u < QCOLS / 8; u++) {
-        const uint4 x = __ldg(a + u), y = __ldg(o + u);
-        delta += bf_lo(x.x) * bf_lo(y.x) + bf_hi(x.x) * bf_hi(y.x) + bf_lo(x.y) * bf_lo(y.y) + bf_hi(x.y) * bf_hi(y.y) +
-                 bf_lo(x.z) * bf_lo(y.z) + bf_hi(x.z) * bf_hi(y.z) + bf_lo(x.w) * bf_lo(y.w) + bf_hi(x.w) * bf_hi(y.w);
-      }
-    }
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + (cq * 128 + row) * 4), "f"(delta) : "memory");
-    named_bar(5, NUM_SM_WARPS * 32);   // key bits and the delta quarters are visible
-    delta = 0.f;
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(sRed + (o * 128 + row) * 4) : "memory");
-      delta += other;
-    }
-    named_bar(5, NUM_SM_WARPS * 32);   // (the exchange area is the dS staging tile: everyone has read before anyone writes)
+    named_bar(5, NUM_SM_WARPS * 32);   // key bits are visible
+    // delta_i = sum_c dO[i,c] O[i,c] over the head (attn_delta_kernel) and the row's log-sum-exp
+    const float delta = row_ok ? p.delta[(int64_t)bh * S + i] : 0.f;
     const float lse = row_ok ? p.lse[(int64_t)bh * S + i] : 1e30f;
     // dS = P (dropout'(dP) - delta) scale with the scales folded: dS = P * fma(dP, ks, -ds) (kept) or P * (-ds) (dropped)
     const float ks = dr.inv_keep * p.scale, dsn = -delta * p.scale;
-    // scatter geometry (rel_shift^T): element (ii, j) -> dBD_raw offset ii (ld - 1) + S - 1 + j (+ dl above the diagonal)
-    const int dl = ld - S - 1;
-    const uint32_t tbuf = sPD + q * 4096 + cq * 1024;   // scratch inside this warp quartet's rows of the Pd staging tile
     int nb = 0;
     auto take_bias = [&](uint32_t (&w)[8], int jt, bool upper) {
       mbar_wait(b_full, nb & 1);
@@ -749,38 +738,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // ---- outputs.  The staging tiles are free once the previous tile's dQu MMA and tensor stores have read them ----
       if (t > 0) mbar_wait(out_empty, (t - 1) & 1);
       if (tr) A3T_TRACE(0, 8 * t + 4);
-      // dBD_raw = rel_shift^T(dS): thread-per-query registers -> scratch -> lanes along the key axis, 2-byte stores
-      // (rows of dBD_raw shift by one element per query: no wider aligned store exists); two queries per instruction
-      {
-        const int c = lane & 15, rr = lane >> 4;
-        const int j = j0 + c;
-        const bool j_ok = j < S;
-        unsigned short* const pl = dbd + j;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {        // 16 queries at a time
-          if ((lane >> 4) == half) {
-#pragma unroll
-            for (int u = 0; u < 2; u++)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + (lane & 15) * 48 + 16 * u), "r"(dsw[4 * u]),
-                           "r"(dsw[4 * u + 1]), "r"(dsw[4 * u + 2]), "r"(dsw[4 * u + 3])
-                           : "memory");
-          }
-          __syncwarp();
-          const int ii0 = i0 + q * 32 + half * 16 + rr;
-          int arow = ii0 * (ld - 1) + S - 1;      // offset of (ii, 0) through the lower band
-#pragma unroll
-          for (int it = 0; it < 8; it++) {
-            const int ii = ii0 + 2 * it;
-            unsigned short v;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tbuf + (2 * it + rr) * 48 + 2 * c) : "memory");
-            if (j_ok && ii < S && j != ii + 1) pl[arow + (j > ii ? dl : 0)] = v;
-            arow += 2 * (ld - 1);
-          }
-          __syncwarp();
-        }
-      }
-      named_bar(1 + q, 128);   // the other warps' scratch lives in the same rows of the staging tile
-      if (tr) A3T_TRACE(0, 8 * t + 5);
       const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
       for (int u = 0; u < 2; u++) {
@@ -796,6 +753,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(out_full);
+      if (tr) A3T_TRACE(0, 8 * t + 5);
+      mbar_wait(out_full, t & 1);   // every warp's rows are staged
+#pragma unroll
+      for (int half = 0; half < 2; half++) {                // keys 32 half .. +31 of the tile
+        const int j = t * 64 + 32 * half + lane;
+        const bool j_ok = j < S;
+        unsigned short* const pl = dbd + j;
+        const uint32_t cb = (uint32_t)(2 * (32 * half + lane));   // byte offset of the key inside a 128-byte row
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const int rowl = 8 * warp + r, ii = i0 + rowl;
+          unsigned short v;
+          asm volatile("ld.shared.u16 %0, [%1];"
+                       : "=h"(v)
+                       : "r"(sDS + rowl * 128 + ((((cb >> 4) ^ (uint32_t)(rowl & 7)) << 4) | (cb & 15u)))
+                       : "memory");
+          if (j_ok && ii < S && j != ii + 1) pl[ii * (ld - 1) + S - 1 + (j > ii ? dl : 0)] = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_empty);
       if (tr) A3T_TRACE(0, 8 * t + 6);
     }
     // ---- epilogue: d(q+u) -> dqkv4[:, :, h*dk ...] ----
@@ -836,6 +814,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// delta[b,h,i] = sum_c dO[b,i,h*dk+c] * O[b,i,h*dk+c]: one warp per (b, i), lanes along the row
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx,
+                                                         float* __restrict__ delta, int B, int H, int S, int D) {
+  A3T_PDL_TRIGGER();
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= (int64_t)B * S) return;
+  const int dk = D / H;
+  const uint4* a = reinterpret_cast<const uint4*>(dctx + r * D);
+  const uint4* o = reinterpret_cast<const uint4*>(ctx + r * D);
+  const int b = (int)(r / S), i = (int)(r - (int64_t)b * S);
+  for (int h = 0; h < H; h++) {
+    float acc = 0.f;
+    for (int u = lane; u < dk / 8; u += 32) {
+      const uint4 x = __ldg(a + h * (dk / 8) + u), y = __ldg(o + h * (dk / 8) + u);
+      acc += bf_lo(x.x) * bf_lo(y.x) + bf_hi(x.x) * bf_hi(y.x) + bf_lo(x.y) * bf_lo(y.y) + bf_hi(x.y) * bf_hi(y.y) +
+             bf_lo(x.z) * bf_lo(y.z) + bf_hi(x.z) * bf_hi(y.z) + bf_lo(x.w) * bf_lo(y.w) + bf_hi(x.w) * bf_hi(y.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) delta[((int64_t)b * H + h) * S + i] = acc;
   }
 }
 
@@ -949,13 +950,13 @@ extern "C" int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t
 }
 
 extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, const void* ctx,
-                                   const void* dctx, const float* lse, void* dqkv4, void* pd, void* ds, void* dbd, int B, int H,
-                                   int S, int D, float scale, float drop_p, const unsigned long long* seed, uint32_t site,
-                                   void* stream) {
+                                   const void* dctx, const float* lse, float* delta_ws, void* dqkv4, void* pd, void* ds, void* dbd,
+                                   int B, int H, int S, int D, float scale, float drop_p, const unsigned long long* seed,
+                                   uint32_t site, void* stream) {
   using namespace fa;
   int rc = check_common("relpos_attn_bwd", qkv4, bd_raw, keymask, B, H, S, D, ld, drop_p, seed);
   if (rc) return rc;
-  A3T_REQUIRE(ctx && dctx && lse && dqkv4 && pd && ds && dbd, "relpos_attn_bwd: null pointer");
+  A3T_REQUIRE(ctx && dctx && lse && delta_ws && dqkv4 && pd && ds && dbd, "relpos_attn_bwd: null pointer");
   A3T_REQUIRE(((((uintptr_t)ctx) | ((uintptr_t)dctx) | ((uintptr_t)dqkv4) | ((uintptr_t)ds)) & 15) == 0 && (ld % 8) == 0,
               "relpos_attn_bwd: 16-byte alignment / pitch multiple of 8");
   const int dk = D / H;
@@ -975,7 +976,11 @@ extern "C" int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t
   memset(&p, 0, sizeof(p));
   p.bd_raw = (const __nv_bfloat16*)bd_raw; p.keymask = keymask; p.seed = seed; p.lse = const_cast<float*>(lse);
   p.ctx = (__nv_bfloat16*)const_cast<void*>(ctx); p.dctx = (const __nv_bfloat16*)dctx; p.dq = (__nv_bfloat16*)dqkv4;
-  p.pd = (__nv_bfloat16*)pd; p.dbd = (__nv_bfloat16*)dbd;
+  p.pd = (__nv_bfloat16*)pd; p.dbd = (__nv_bfloat16*)dbd; p.delta = delta_ws;
+  attn_delta_kernel<<<(unsigned)(((int64_t)B * S + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dctx, (const __nv_bfloat16*)ctx,
+                                                                                         delta_ws, B, H, S, D);
+  rc = check_launch("relpos_attn_bwd(delta)");
+  if (rc) return rc;
   p.ld = ld; p.B = B; p.H = H; p.S = S; p.D = D; p.scale = scale; p.c2 = scale * 1.4426950408889634f; p.drop_p = drop_p;
   p.site = site;
   p.trace = g_trace;

@@ -194,16 +194,20 @@ int a3t_embed_assemble_bwd(const float* dxs, const int64_t* text, const int64_t*
  *      log2-domain log-sum-exp of the scaled scores (1e30 for a row without a valid key).
  * bwd: given dctx (B,S,D) bf16: d(q+u) -> dqkv4[..., h*dk ..] (columns [0,D) of the (B,S,4D) bf16 buffer), and the
  *      operands of the remaining contractions, each written once, (B,H,S,ld) bf16: pd = dropped probabilities,
- *      ds = d scores (scaled), dbd = rel_shift^T(ds) (= d bd_raw).  ld % 8 == 0.
+ *      ds = d scores (scaled), dbd = rel_shift^T(ds) (= d bd_raw).  ld % 8 == 0.  delta_ws: caller-owned (B,H,S) fp32
+ *      workspace (row sums of dctx * ctx per head, written by a small pre-kernel of the same call).
  * Dropout element index = ((b*H + h)*S + i)*S + j (the contiguous (B,H,S,S) view), as the unfused kernels use.
  * a3t_attn_fused_supported: 1 if (B,H,S,D) qualifies (D/H in {64,128,192}, B*H*S*S < 2^32). */
 int a3t_attn_fused_supported(int B, int H, int S, int D);
+/* Tuning builds (-DA3T_TUNING) only: device buffer of 8 x 256 int64 that CTA 0 of the next fused-attention
+ * launches fills with clock64 stamps per warp role (NULL switches it off; release builds ignore it). */
+int a3t_attn_set_trace(void* device_buffer);
 int a3t_relpos_attn_fwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask, void* ctx,
                         float* lse, int B, int H, int S, int D, float scale, float drop_p,
                         const unsigned long long* seed, uint32_t site, void* stream);
 int a3t_relpos_attn_bwd(const void* qkv4, const void* bd_raw, int64_t ld, const uint8_t* keymask,
-                        const void* ctx, const void* dctx, const float* lse, void* dqkv4, void* pd, void* ds,
-                        void* dbd, int B, int H, int S, int D, float scale, float drop_p,
+                        const void* ctx, const void* dctx, const float* lse, float* delta_ws, void* dqkv4,
+                        void* pd, void* ds, void* dbd, int B, int H, int S, int D, float scale, float drop_p,
                         const unsigned long long* seed, uint32_t site, void* stream);
 
 /* Legacy relative-position masked softmax (transformer/attention.py:145-165 rel_shift, :205-207

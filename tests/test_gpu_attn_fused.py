@@ -120,8 +120,9 @@ def test_fused_attention_dropout_pattern_is_the_unfused_one(tc):
     dq = torch.empty_like(qc)
     pr, seed, site = tc._drop((0.3, 11))
     dctx = torch.zeros(B, S, D, dtype=torch.bfloat16, device="cuda")
+    delta = torch.empty(B, H, S, dtype=torch.float32, device="cuda")
     _lib.call("a3t_relpos_attn_bwd", qc.data_ptr(), bd.data_ptr(), bd.stride(2), kc.view(torch.uint8).data_ptr(), ctx.data_ptr(),
-              dctx.data_ptr(), lse.data_ptr(), dq.data_ptr(), pd2.data_ptr(), ds.data_ptr(), dbd.data_ptr(), B, H, S, D, scale, pr,
+              dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), pd2.data_ptr(), ds.data_ptr(), dbd.data_ptr(), B, H, S, D, scale, pr,
               seed, site, torch.cuda.current_stream().cuda_stream)
     a, b = Pd.float().cpu(), pd2.float().cpu()
     big = Pm.float().cpu() > 1e-4                    # where the undropped probability is not rounding noise

@@ -16,13 +16,14 @@ ctx, bd, lse = tc.attn_fwd_fused(qkv4, p, km, H, sc, drop=drop)
 dctx = torch.randn_like(ctx)
 dq = torch.empty_like(qkv4)
 pd, ds, dbd = tc._like(bd), tc._like(bd), tc._like(bd)
+delta = torch.empty(B, H, S, dtype=torch.float32, device='cuda')
 pr, seed, site = tc._drop(drop)
 st = torch.cuda.current_stream().cuda_stream
 kmu = km.view(torch.uint8)
 def fwd():
     _lib.call("a3t_relpos_attn_fwd", qkv4.data_ptr(), bd.data_ptr(), bd.stride(2), kmu.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, H, S, D, sc, pr, seed, site, st)
 def bwd():
-    _lib.call("a3t_relpos_attn_bwd", qkv4.data_ptr(), bd.data_ptr(), bd.stride(2), kmu.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), dq.data_ptr(), pd.data_ptr(), ds.data_ptr(), dbd.data_ptr(), B, H, S, D, sc, pr, seed, site, st)
+    _lib.call("a3t_relpos_attn_bwd", qkv4.data_ptr(), bd.data_ptr(), bd.stride(2), kmu.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), pd.data_ptr(), ds.data_ptr(), dbd.data_ptr(), B, H, S, D, sc, pr, seed, site, st)
 for name, f in (("fwd", fwd), ("bwd", bwd)):
     for _ in range(3): f()
     torch.cuda.synchronize()
