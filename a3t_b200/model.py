@@ -353,6 +353,23 @@ class ESPnetMLMModel(_ModelBase):
         return dict(feat_gen=outs)
 
 
+    def inference_batch(self, speech, text, masked_position, speech_mask, text_mask, speech_segment_pos,
+                        text_segment_pos, span_boundary, **unused):
+        """Batched form of `inference` (the reference edits one utterance per call, sedit_model.py:239-284;
+        BASELINE configs[4] asks for 32): ONE forward over (B, Ts, ...) and the stitching
+        `[orig[:s], generated[s:e], orig[e:]]` for every utterance at once.  span_boundary: B pairs [s, e].
+        Returns the stitched mels (B, Ts, odim); row b equals torch.cat(inference(...)["feat_gen"]) of utterance b."""
+        batch = dict(speech_pad=speech, text_pad=text, masked_position=masked_position, speech_mask=speech_mask,
+                     text_mask=text_mask, speech_segment_pos=speech_segment_pos, text_segment_pos=text_segment_pos)
+        with torch.no_grad():
+            before, after, _, _ = self._forward(batch, speech_segment_pos)
+        gen = after if after is not None else before
+        sb = torch.as_tensor(span_boundary, device=speech.device).reshape(speech.shape[0], 2)
+        t = torch.arange(speech.shape[1], device=speech.device)[None, :]
+        inside = (t >= sb[:, :1]) & (t < sb[:, 1:])
+        return torch.where(inside.unsqueeze(-1), gen.to(speech.dtype), speech)
+
+
 class ESPnetMLMEncAsDecoderModel(ESPnetMLMModel):
     """espnet2/tts/sedit/sedit_model.py:348-375 (the paper model)."""
 

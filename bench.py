@@ -2,7 +2,8 @@
 """Benchmark of the A3T masked-mel training hot path (BASELINE.json metric: mel-frames/s of training).
 
   python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, one process per GPU)
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+  python bench.py --impl reference --steps K --warmup W    # the reference's own modules (oracle/_ref snapshot) on host cores
+  python bench.py --config cfg4 | cfg5                     # BASELINE configs[3] per-GPU shape / configs[4] (infill + vocoder)
 
 A "step" = forward + backward + gradient all-reduce + clip/Adam/Noam of `ESPnetMLMEncAsDecoderModel`
 on one synthetic batch per GPU.  Workload = BASELINE configs[1] ("cfg2"): the VCTK paper Conformer
@@ -198,6 +199,20 @@ def _time_gemms(fn):
     evs = []
 
     def timing(name, *a):
+        if name in ("a3t_relpos_attn_fwd", "a3t_relpos_attn_bwd"):
+            # fused attention: QK^T + PV (fwd), QK^T + dO V^T + dS K (bwd) per (b, h); operands in, ctx / lse (fwd) or the
+            # three (B,H,S,S) operands of the remaining contractions (bwd) out
+            fwd = name.endswith("fwd")
+            Bn, H, S, D = (a[6:10] if fwd else a[12:16])
+            dk = D // H
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = orig(name, *a)
+            e1.record()
+            fl = (4.0 if fwd else 6.0) * Bn * H * S * S * dk
+            by = 2.0 * Bn * H * S * S * (1 if fwd else 4) + 2.0 * Bn * S * D * (4 if fwd else 7)
+            evs.append((e0, e1, fl, by, "fused rel-pos attention (scores on chip)"))
+            return rc
         if name != "a3t_gemm":
             return orig(name, *a)
         d = a[0]
@@ -214,7 +229,7 @@ def _time_gemms(fn):
         else:
             by = nb * (2 * d.M * d.K + 2 * d.N * d.K + cs * d.M * d.N)
         if nb > 1:
-            cls = "attention (batched QK^T / PV and their gradients)"
+            cls = "attention (batched BD_raw = (q+v) p^T, dV, dK, d(q+v), dp)"
         elif d.taps == 3:
             cls = "ffn conv k3 (fwd, dgrad, wgrad)"
         elif d.taps == 1:
@@ -241,33 +256,75 @@ def _time_gemms(fn):
     return ms, sum(f for _, _, f, _, _ in evs), len(evs), sum(b for _, _, _, b, _ in evs), by_class
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's path (same op graph, torch CPU fp32, autograd backward),
-    on all host threads, on a bounded sample of the cfg2 workload."""
-    from a3t_b200 import graph
-    from a3t_b200.model import build_model
-    from oracle.oracle_backend import OracleBackend
+def _clean_thread_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its children: a CPU baseline timed under it is noise."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        env.pop(k, None)
+    return env
 
+
+def run_reference(args):
+    """CPU arm: the REFERENCE's own modules (oracle/_ref: a verbatim snapshot of the files the path imports, made by
+    oracle/build_ref.py) -- MLMTask.build_model with conf/fsp2_conformer.yaml, the reference collate helpers for the
+    batch, `loss = model(**batch)[0]; loss.backward()` in train mode (dropout on), fp32, all host threads -- on a
+    bounded sample of the cfg2 workload (B = --cpu-batch of the 16 utterances; the model and frame counts are the
+    full ones).  Falls back to the oracle port of the same graph when the snapshot is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    omp = os.environ.get("OMP_NUM_THREADS")
+    if omp is not None and int(omp) < cores and os.environ.get("A3T_REF_CHILD") != "1":
+        env = _clean_thread_env()
+        env["A3T_REF_CHILD"] = "1"
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, capture_output=True, text=True)
+        sys.stdout.write(r.stdout)
+        sys.stderr.write(r.stderr[-2000:])
+        return
     torch.set_num_threads(cores)
-    enc, dec, mc = paper_conf()
-    torch.manual_seed(0)
-    m = build_model(enc, dec, mc)
     Bs = args.cpu_batch
-    hb = expand_on_host(synthetic_batch_host(Bs, args.frames, args.phones, seed=0))
-    ops = OracleBackend(seed=1, autograd=True)
-    P = {n: p for n, p in m.named_parameters()}
-    P.update({n: b for n, b in m.named_buffers()})
+    from oracle import build_ref
 
-    def step():
-        for p in m.parameters():
-            p.grad = None
-        loss, _, _, _ = graph.forward(ops, P, graph.WeightCache(), m.cfg, hb, True, True)
-        loss.backward()
-        return float(loss)
+    if build_ref.available():
+        os.environ["A3T_REFERENCE_ROOT"] = build_ref.OUT
+        from oracle import ref_harness as R
+
+        R.REFERENCE_ROOT = build_ref.OUT
+        conf = R.model_conf("paper")
+        m = R.build_reference_model(conf, seed=0)
+        with torch.no_grad():  # as the GPU arm: BatchNorm gains 1 (xavier init zeroes them) so every layer does real work
+            for n, p in m.named_parameters():
+                if p.dim() == 1 and n.endswith("weight"):
+                    p.fill_(1.0)
+        batch, _ = R.synthetic_batch(Bs, args.frames, args.phones, seed=0)
+        kind = "reference"
+
+        def step():
+            loss, _ = R.reference_step(m, batch, train=True)
+            return float(loss)
+    else:
+        from a3t_b200 import graph
+        from a3t_b200.model import build_model
+        from oracle.oracle_backend import OracleBackend
+
+        enc, dec, mc = paper_conf()
+        torch.manual_seed(0)
+        m = build_model(enc, dec, mc)
+        hb = expand_on_host(synthetic_batch_host(Bs, args.frames, args.phones, seed=0))
+        ops = OracleBackend(seed=1, autograd=True)
+        P = {n: p for n, p in m.named_parameters()}
+        P.update({n: b for n, b in m.named_buffers()})
+        kind = "port"
+
+        def step():
+            for p in m.parameters():
+                p.grad = None
+            loss, _, _, _ = graph.forward(ops, P, graph.WeightCache(), m.cfg, hb, True, True)
+            loss.backward()
+            return float(loss)
 
     for _ in range(args.warmup):
         step()
@@ -276,28 +333,119 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     fps = Bs * args.frames * args.steps / dt
-    sample = f"B={Bs} of {args.batch} utterances x Ts={args.frames}/Tt={args.phones}, {args.steps} step(s), fwd+bwd, fp32, dropout on"
+    sample = (f"B={Bs} of {args.batch} utterances x Ts={args.frames}/Tt={args.phones} (full model, full sequence lengths; "
+              f"frames/s is batch-size independent on a CPU), {args.steps} step(s), fwd+bwd, fp32, dropout on")
     print(json.dumps({
-        "impl": "reference", "metric": "mel-frames/sec training (VCTK A3T Conformer cfg2)", "value": fps,
+        "impl": "reference", "metric": f"mel-frames/sec training (VCTK A3T Conformer {args.config})", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: VCTK paper Conformer 4+4 blocks D=384, Ts=1024, Tt=128 (CPU sample)", "batch": Bs},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": f"{args.config}: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
+                               f"Ts={args.frames}, Tt={args.phones}, train step fwd+bwd, dropout on; CPU sample of B={Bs} of the "
+                               f"{args.batch} utterances per step (same model, same sequence lengths)", "batch": Bs},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def cpu_baseline_leg(args):
-    """Bounded CPU sample on rank 0 (reported beside the GPU number)."""
+    """Bounded CPU sample on rank 0 (reported beside the GPU number); own process, clean thread environment."""
+    env = _clean_thread_env()
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
                         "--cpu-batch", str(args.cpu_batch), "--frames", str(args.frames), "--phones", str(args.phones)],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=env)
     for line in r.stdout.strip().splitlines()[::-1]:
         try:
             return json.loads(line)["cpu_baseline"]
         except Exception:
             continue
     return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+
+
+def parity_object(dev):
+    """Measured deviation of the benchmarked bf16 / tcgen05 path from the fp32 REFERENCE on the paper-width fixture
+    (tests/golden/model_d384.pt: D=384, 1+1 blocks, B=2, Ts=1024, Tt=128; produced by running the reference).
+    A checker, not the product path."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _d384
+        from test_gpu_parity_r2 import bf16_parity_numbers
+
+        fx, b = _d384.load(os.path.join(ROOT, "tests", "golden"))
+        r = bf16_parity_numbers(fx, b)
+        r["fixture"] = "tests/golden/model_d384.pt (reference-generated), IMPL_TC, dropout 0"
+        r["fp32_gate"] = "fp32 kernels meet |dloss| <= 1e-4 |loss| on the same fixture (tests/test_gpu_parity_r2.py)"
+        return r
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
+def run_cfg5(args):
+    """BASELINE configs[4]: speech-editing inference -- masked-mel infill of 32 utterances (Ts=1024, Tt=128, span [384,640))
+    in ONE batched call of the model + ParallelWaveGAN on 32 x 1024 frames -> 32 x 307 200 samples."""
+    from a3t_b200 import _lib
+    from a3t_b200.model import build_model
+    from a3t_b200.vocoder import ParallelWaveGANGenerator
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    enc, dec, mc = paper_conf()
+    torch.manual_seed(0)
+    model = build_model(enc, dec, mc, act_dtype=torch.bfloat16)
+    model.gemm_impl = _lib.IMPL_TC
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and n.endswith("weight"):
+                p.fill_(1.0)
+    B, Ts, Tt, hop, fs = 32, 1024, 128, 300, 24000
+    host = synthetic_batch_host(B, Ts, Tt, seed=0)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    gen = ParallelWaveGANGenerator(upsample_params={"upsample_scales": [4, 5, 3, 5]}).to(dev).eval()
+    z = torch.randn(B, 1, Ts * hop, device=dev)
+    span = [[384, 640]] * B
+
+    def infill():
+        b = device_batch(pinned, dev)
+        b["masked_position"] = torch.zeros(B, Ts, dtype=torch.bool, device=dev)
+        b["masked_position"][:, 384:640] = True
+        return model.inference_batch(**b, span_boundary=span)
+
+    def one():
+        mel = infill()                                   # (B, Ts, 80): original frames outside the span, generated inside
+        return gen.generate(mel.transpose(1, 2).contiguous(), z)
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        wav = one()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_inf = t_all = 0.0
+    for _ in range(args.steps):
+        ev[0].record()
+        mel = infill()
+        ev[1].record()
+        wav = gen.generate(mel.transpose(1, 2).contiguous(), z)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_inf += ev[0].elapsed_time(ev[1])
+        t_all += ev[0].elapsed_time(ev[2])
+    clk = clocks.stop()
+    ms = t_all / args.steps
+    audio_s = B * Ts * hop / fs
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    print(json.dumps({
+        "metric": "speech-editing inference: masked-mel infill + ParallelWaveGAN, real-time factor", "value": ms / 1e3 / audio_s,
+        "unit": "RTF (s compute / s audio)", "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": False, "scaling": "replicas only", "vs_baseline": None, "dtype": "bf16 (model) / f32 (vocoder)",
+        "data": "synthetic",
+        "config": {"workload": "cfg5: 32 utterances x Ts=1024 / Tt=128, span [384,640), batched infill + PWG 30 layers "
+                               "-> 32 x 307200 samples", "infill_ms": t_inf / args.steps, "vocoder_ms": (t_all - t_inf) / args.steps,
+                   "utterances_per_s": B / (ms / 1e3), "audio_seconds_per_s": audio_s / (ms / 1e3)},
+        "e2e": {"value": ms / 1e3 / audio_s, "unit": "RTF", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 0},
+        "clocks": clk}))
 
 
 def main():
@@ -311,12 +459,21 @@ def main():
     ap.add_argument("--phones", type=int, default=128)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="cfg2: B=16, Ts=1024, Tt=128 per GPU (headline); cfg4: B=8 per GPU (64 over 8 GPUs), Ts=1500, Tt=192; "
+                         "cfg5: batched infill + vocoder inference (own metric)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of untimed back-to-back steps before the timed region")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the frontend / vocoder side measurements")
     args = ap.parse_args()
+    if args.config == "cfg4":
+        args.batch, args.frames, args.phones = 8, 1500, 192
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "cfg5":
+        return run_cfg5(args)
 
     import torch.distributed as dist
     from a3t_b200 import _lib
@@ -334,7 +491,9 @@ def main():
     enc, dec, mc = paper_conf()
     torch.manual_seed(0)
     act = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    model = build_model(enc, dec, mc, act_dtype=act).to(dev).train()
+    model = build_model(enc, dec, mc, act_dtype=act)
+    model.gemm_impl = _lib.IMPL_TC   # a GEMM that does not qualify for the tcgen05 kernel is an error, never a silent fallback
+    model = model.to(dev).train()
     with torch.no_grad():  # xavier init zeroes BatchNorm gamma: give the conv module / postnet real work
         for n, p in model.named_parameters():
             if p.dim() == 1 and n.endswith("weight"):
@@ -383,6 +542,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- at least 2 s of back-to-back steps first: the timed region then runs at the clocks / power state of a long
+    # job (the "sustained" tensor peak is the right denominator), not in the first-second burst
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < args.sustain_s:
+        for _ in range(10):
+            one_step()
+        torch.cuda.synchronize()
     # ---- timed region: K steps, device-timed, max over ranks -----------------------------------
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -427,12 +593,14 @@ def main():
         pass
     traffic, traffic_src = None, None
     try:  # DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        tn = [f for f in ("r02_gemm_traffic.json", "r01_gemm_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", f))][0]
+        tj = json.load(open(os.path.join(ROOT, "profiles", tn)))
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (timed after >= 2 s of steps)" if peaks else "fallback"
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     alg_flops_step = 3.0 * B * fwd_flops_per_sample(Ts, Tt)
 
@@ -448,27 +616,28 @@ def main():
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline_leg(args)
         out = {
-            "metric": "mel-frames/sec training (VCTK A3T Conformer cfg2)", "value": value, "unit": "frames/s",
+            "metric": f"mel-frames/sec training (VCTK A3T Conformer {args.config})", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "cfg2: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
+            "config": {"workload": f"{args.config}: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
                                    f"B={B}/GPU, Ts={Ts}, Tt={Tt}, train step fwd+bwd+allreduce+clip/Adam/Noam, dropout on",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": used_graph,
                        "graph_error": graph_err, "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                        "loss": loss_now, "alg_tflop_per_step_per_gpu": alg_flops_step / 1e12,
                        "step_tensor_frac_of_peak": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / peak},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_unit": "B/launch (DRAM read+write, mean over the step's GEMM launches)",
+                         "frac": achieved / peak if peak else None, "frac_of_burst_peak": achieved / peak_burst, "traffic": traffic, "traffic_unit": "B/launch (DRAM read+write, mean over the step's GEMM launches)",
                          "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
                          "algorithmic_flop_per_launch": gemm_flops / max(n_gemm, 1),
                          "by_class": {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] / 1e3) / 1e12 if v[1] > 0 else None,
                                           "frac": (v[2] / (v[1] / 1e3) / 1e12 / peak) if v[1] > 0 and peak else None}
                                       for k, v in gemm_classes.items()},
-                         "kernel": "a3t_gemm (all dense contractions of the step)", "launches": n_gemm,
+                         "kernel": "tc::gemm_tc_kernel (a3t_gemm) + fa::attn_{fwd,bwd}_kernel: all dense contractions of the step",
+                         "launches": n_gemm,
                          "how": "CUDA-event pair around every a3t_gemm call of one eager step (GPU kept busy ahead of the host so the pairs hold kernel time only); FLOPs = 2*M*N*K*batch per call",
                          "peak_source": peak_src},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity": None if args.no_parity else parity_object(dev),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
             "gpu_launches": counts["kernels"] * args.steps, "clocks": clk, "aux": aux,
         }
