@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(256) segment_pos_kernel(const int32_t* __restr
 
 using namespace a3t;
 
+namespace a3t {
+int stft_logmel_regfft(const float* wav, const int64_t* ilens, const float* window, const float* melmat,
+                       const int32_t* mel_range, float* mel, int B, int64_t N, int T, int n_fft, int win_length, int hop,
+                       int n_mels, cudaStream_t st);
+}
+
 extern "C" int a3t_stft_logmel(const float* wav, const int64_t* ilens, const float* window, const float* melmat,
                                const int32_t* mel_range, float* mel, int64_t* olens, int B, int64_t N, int n_fft,
                                int win_length, int hop, int n_mels, void* stream) {
@@ -214,12 +220,16 @@ extern "C" int a3t_stft_logmel(const float* wav, const int64_t* ilens, const flo
   if (B == 0) return A3T_OK;
   const int T = (int)(1 + N / hop);
   const int NC = n_fft / 2;
-  size_t smem = (size_t)2 * NC * sizeof(float2) + (size_t)(NC + 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(stft_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  stft_logmel_kernel<<<B * T, FE_THREADS, smem, st>>>(wav, ilens, window, melmat, mel_range, mel, B, N, T, n_fft,
-                                                      win_length, hop, n_mels);
-  int rc = check_launch("stft_logmel");
+  // warp-per-frame register FFT for the recipe sizes (n_fft 2048 / 1024); the shared-memory Stockham kernel otherwise
+  int rc = stft_logmel_regfft(wav, ilens, window, melmat, mel_range, mel, B, N, T, n_fft, win_length, hop, n_mels, st);
+  if (rc == A3T_ERR_UNSUPPORTED) {
+    size_t smem = (size_t)2 * NC * sizeof(float2) + (size_t)(NC + 1) * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(stft_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stft_logmel_kernel<<<B * T, FE_THREADS, smem, st>>>(wav, ilens, window, melmat, mel_range, mel, B, N, T, n_fft,
+                                                        win_length, hop, n_mels);
+    rc = check_launch("stft_logmel");
+  }
   if (rc) return rc;
   if (olens) {
     olens_kernel<<<(B + 127) / 128, 128, 0, st>>>(ilens, olens, B, N, win_length, hop);
