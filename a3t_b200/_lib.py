@@ -98,6 +98,9 @@ _SIGS = {
     "a3t_segment_pos": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "a3t_pwg_upsample": [_P, _P, _P, _I, _L, _I, _P],
     "a3t_pwg_conv1d": [_P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _I, _I, _F, _P],
+    "a3t_pwg_last": [_P, _P, _P, _P, _P, _P, _I, _L, _F, _P],
+    "a3t_pwg_split_planes": [_P, _P, _P, _I, _I, _L, _P],
+    "a3t_pwg_resblock_tc": [_P] * 13 + [_I, _L, _I, _I, _P],
     "a3t_pwg_resblock": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
 }
 # entry points that return a count / flag rather than a status code

@@ -60,6 +60,9 @@ class ParallelWaveGANGenerator(nn.Module):
             self.conv_layers.append(blk)
         self.last_conv_layers = nn.ModuleList([nn.ReLU(), nn.Conv1d(S, S, 1), nn.ReLU(), nn.Conv1d(S, 1, 1)])
         self._packed = None
+        self._packed_tc = None
+        self.use_tensor_cores = True   # False: the fp32 CUDA-core residual block (csrc/pwg.cu)
+        self.tc_passes = 3             # 3: full split-fp16 products; 2: weights as single fp16 (see include/a3t_b200.h)
 
     # K-major weight packs for the fused residual-block kernel (rebuilt when parameters change)
     def _packs(self):
@@ -75,6 +78,32 @@ class ParallelWaveGANGenerator(nn.Module):
             packs.append((w_in_t, blk.conv.bias.detach().float().contiguous(), w_out_t,
                           blk.conv1x1_out.bias.detach().float().contiguous()))
         self._packed = (sig, packs)
+        return packs
+
+    @staticmethod
+    def _split16(w: torch.Tensor):
+        """fp32 -> (hi, lo) fp16 with hi + lo = w to 22 mantissa bits."""
+        hi = w.to(torch.float16)
+        lo = (w - hi.float()).to(torch.float16)
+        return hi.contiguous(), lo.contiguous()
+
+    def _packs_tc(self):
+        """Split-fp16 K-major weight packs of the tensor-core residual block (csrc/pwg_tc.cu):
+        W1 (128, 320) = [tap0 | tap1 | tap2 | aux 80 | 48 zeros] stored as 5 contiguous (128, 64) K chunks, W2 (128, 64)."""
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed_tc is not None and self._packed_tc[0] == sig:
+            return self._packed_tc[1]
+        packs = []
+        for blk in self.conv_layers:
+            wc = blk.conv.weight.detach().float()                       # (128, 64, 3)
+            wa = blk.conv1x1_aux.weight.detach().float()[:, :, 0]       # (128, 80)
+            w1 = torch.zeros(128, 320, dtype=torch.float32, device=wc.device)
+            w1[:, 0:64], w1[:, 64:128], w1[:, 128:192], w1[:, 192:272] = wc[:, :, 0], wc[:, :, 1], wc[:, :, 2], wa
+            w2 = blk.conv1x1_out.weight.detach().float()[:, :, 0].contiguous()   # (128, 64): rows 0..63 residual, 64..127 skip
+            w1 = w1.view(128, 5, 64).permute(1, 0, 2).contiguous()      # chunk-major (5, 128, 64): each K chunk contiguous
+            packs.append(self._split16(w1) + self._split16(w2)
+                         + (blk.conv.bias.detach().float().contiguous(), blk.conv1x1_out.bias.detach().float().contiguous()))
+        self._packed_tc = (sig, packs)
         return packs
 
     @torch.no_grad()
@@ -105,21 +134,35 @@ class ParallelWaveGANGenerator(nn.Module):
         x = torch.empty(B, 64, Tw, device=dev)
         _lib.call("a3t_pwg_conv1d", z.data_ptr(), self.first_conv.weight.data_ptr(), self.first_conv.bias.data_ptr(),
                   x.data_ptr(), B, 1, 64, Tw, 1, 1, 0, 0, 1.0, st)
-        x2 = torch.empty_like(x)
         skip = torch.empty(B, 64, Tw, device=dev)
         per = self.layers // self.stacks
-        for l, (w_in_t, b_in, w_out_t, b_out) in enumerate(self._packs()):
-            _lib.call("a3t_pwg_resblock", x.data_ptr(), cc.data_ptr(), w_in_t.data_ptr(), b_in.data_ptr(),
-                      w_out_t.data_ptr(), b_out.data_ptr(), x2.data_ptr(), skip.data_ptr(), B, Tw, 64, 128, 80, 64,
-                      2 ** (l % per), int(l == 0), st)
-            x, x2 = x2, x
+        if self.use_tensor_cores:
+            # tcgen05 residual blocks on split-fp16 planes (hi + lo = 22 mantissa bits), channels-last (B, T, C)
+            planes = lambda ch_: (torch.empty(B, Tw, ch_, dtype=torch.float16, device=dev),
+                                  torch.empty(B, Tw, ch_, dtype=torch.float16, device=dev))
+            ch, cl = planes(80)
+            _lib.call("a3t_pwg_split_planes", cc.data_ptr(), ch.data_ptr(), cl.data_ptr(), B, 80, Tw, st)
+            del cc
+            xh, xl = planes(64)
+            _lib.call("a3t_pwg_split_planes", x.data_ptr(), xh.data_ptr(), xl.data_ptr(), B, 64, Tw, st)
+            del x
+            yh, yl = planes(64)   # ping-pong: a block reads the halo of neighbouring tiles
+            for l, (w1h, w1l, w2h, w2l, b1, b2) in enumerate(self._packs_tc()):
+                _lib.call("a3t_pwg_resblock_tc", xh.data_ptr(), xl.data_ptr(), ch.data_ptr(), cl.data_ptr(), w1h.data_ptr(),
+                          w1l.data_ptr(), w2h.data_ptr(), w2l.data_ptr(), b1.data_ptr(), b2.data_ptr(), yh.data_ptr(),
+                          yl.data_ptr(), skip.data_ptr(), B, Tw, 2 ** (l % per), int(l == 0) | (2 if self.tc_passes == 2 else 0), st)
+                xh, xl, yh, yl = yh, yl, xh, xl
+        else:
+            x2 = torch.empty_like(x)
+            for l, (w_in_t, b_in, w_out_t, b_out) in enumerate(self._packs()):
+                _lib.call("a3t_pwg_resblock", x.data_ptr(), cc.data_ptr(), w_in_t.data_ptr(), b_in.data_ptr(),
+                          w_out_t.data_ptr(), b_out.data_ptr(), x2.data_ptr(), skip.data_ptr(), B, Tw, 64, 128, 80, 64,
+                          2 ** (l % per), int(l == 0), st)
+                x, x2 = x2, x
         l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
-        y = torch.empty(B, 64, Tw, device=dev)
-        _lib.call("a3t_pwg_conv1d", skip.data_ptr(), l1.weight.data_ptr(), l1.bias.data_ptr(), y.data_ptr(), B, 64, 64,
-                  Tw, 1, 1, 0, 1, math.sqrt(1.0 / self.layers), st)
         out = torch.empty(B, 1, Tw, device=dev)
-        _lib.call("a3t_pwg_conv1d", y.data_ptr(), l3.weight.data_ptr(), l3.bias.data_ptr(), out.data_ptr(), B, 64, 1,
-                  Tw, 1, 1, 0, 1, 1.0, st)
+        _lib.call("a3t_pwg_last", skip.data_ptr(), l1.weight.data_ptr(), l1.bias.data_ptr(), l3.weight.data_ptr(),
+                  l3.bias.data_ptr(), out.data_ptr(), B, Tw, math.sqrt(1.0 / self.layers), st)
         return out
 
     def forward(self, c: torch.Tensor, z: Optional[torch.Tensor] = None) -> torch.Tensor:

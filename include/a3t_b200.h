@@ -329,6 +329,26 @@ int a3t_pwg_resblock(const float* x, const float* c, const float* w_in_t, const 
                      const float* w_out_t, const float* b_out, float* x_out, float* skip, int B,
                      int64_t T, int R, int G, int A, int S_, int dil, int first, void* stream);
 
+/* Fused output stack of the generator (parallel_wavegan.py:119-126, 166-173):
+ *   out[b,t] = w2 . relu(W1 relu(skip[b,:,t] * scale) + b1) + b2,  skip (B,64,T) fp32, W1 (64,64), w2 (64), out (B,T). */
+int a3t_pwg_last(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                 int B, int64_t T, float scale, void* stream);
+
+/* The same residual block on the tensor cores (csrc/pwg_tc.cu): tcgen05 split-fp16 GEMMs (every operand as hi + lo
+ * fp16 planes, three MMAs per product, fp32 accumulation in TMEM) so that the waveform stays within atol 1e-4 of the
+ * fp32 reference after 30 blocks.  Activations are CHANNELS-LAST planes: xh/xl (B,T,64) in, yh/yl (B,T,64) out (must
+ * not alias the input), ch/cl (B,T,80) conditioning; skip (B,64,T) fp32 channel-major (written when first != 0,
+ * accumulated otherwise); w1h/w1l (5,128,64) fp16 = K chunks [tap0 | tap1 | tap2 | aux 0..63 | aux 64..79 + zeros] of
+ * the (128, 320) gate weight, w2h/w2l (128,64); b1/b2 (128) fp32.
+ * flags: bit 0 = first block (skip is written, not accumulated); bit 1 = two-pass mode: the weights enter as single
+ * fp16 ((x_hi + x_lo) * w_hi, the lo weight planes are not read): 2/3 of the MMAs and 3/4 of the operand traffic, weight
+ * rounding 2^-12 instead of 2^-23.
+ * a3t_pwg_split_planes: fp32 channel-major (B,C,T) -> channels-last hi / lo fp16 planes (B,T,C), C % 8 == 0. */
+int a3t_pwg_split_planes(const float* src, void* hi, void* lo, int B, int C, int64_t T, void* stream);
+int a3t_pwg_resblock_tc(const void* xh, const void* xl, const void* ch, const void* cl, const void* w1h,
+                        const void* w1l, const void* w2h, const void* w2l, const float* b1, const float* b2,
+                        void* yh, void* yl, float* skip, int B, int64_t T, int dil, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

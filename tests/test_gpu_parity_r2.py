@@ -258,9 +258,14 @@ def test_pwg30_matches_reference(golden_dir, cuda_lib):
     gen.load_reference_state_dict(sd)
     gen = gen.cuda()
     z = _d384.pwg30_z(f)
-    y = gen(f["c"].cuda(), z.cuda())
-    err = float((y.cpu() - f["wav"]).abs().max())
-    assert torch.allclose(y.cpu(), f["wav"], atol=1e-4, rtol=1e-4), err
+    # tcgen05 split-fp16 residual blocks (default: 3 MMAs per product), the 2-pass variant (weights as single fp16),
+    # and the fp32 CUDA-core kernel
+    for tc_path, passes in ((True, 3), (True, 2), (False, 3)):
+        gen.use_tensor_cores, gen.tc_passes = tc_path, passes
+        y = gen(f["c"].cuda(), z.cuda())
+        err = float((y.cpu() - f["wav"]).abs().max())
+        print("pwg30 max abs err", f"tensor cores, {passes} passes" if tc_path else "cuda cores", err)
+        assert torch.allclose(y.cpu(), f["wav"], atol=1e-4, rtol=1e-4), (tc_path, passes, err)
 
 
 # ------------------------------------------------------------------------------------------------
