@@ -449,10 +449,13 @@ def forward(ops, P: Dict[str, torch.Tensor], wc: WeightCache, cfg: A3TConfig, ba
 
 
 def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: torch.Tensor,
-             dbefore_ext=None, dafter_ext=None, gout=None) -> Dict[str, torch.Tensor]:
+             dbefore_ext=None, dafter_ext=None, gout=None, on_ready=None) -> Dict[str, torch.Tensor]:
     """Gradients of all parameters given d loss (and optionally extra grads on before/after).
     gout: optional {parameter name: zeroed fp32 buffer of the parameter's shape}; weight gradients are then
-    written in place (G[name] aliases it) instead of into fresh tensors."""
+    written in place (G[name] aliases it) instead of into fresh tensors.
+    on_ready: optional callback(G) invoked after every section of the backward sweep (postnet + head, each
+    decoder block, each encoder block) with the gradients finished so far -- the data-parallel trainer uses it
+    to start the gradient exchange of finished parameter ranges while the sweep continues."""
     sv = ctx.saved
     training = ctx.training
     G = _GradOut(P, gout)
@@ -497,11 +500,13 @@ def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: t
     dx, dg, db = ops.ln_bwd(dz, sv["dec_x"], sv["dec_mean"], sv["dec_rstd"], P["decoder.after_norm.weight"],
                             P["decoder.after_norm.bias"], eps=1e-12)
     G["decoder.after_norm.weight"], G["decoder.after_norm.bias"] = dg, db
-    nl = cfg.enc_blocks + cfg.dec_blocks
+    ready = on_ready if on_ready is not None else (lambda g: None)
+    ready(G)
     for l in reversed(range(cfg.dec_blocks)):
         dx = _layer_bwd(ops, P, wc, f"decoder.encoders.{l}", dx, sv["pos_d"], cfg.H, cfg.dec_dropout,
                         cfg.dec_att_dropout, training, ctx.layers[cfg.enc_blocks + l], G)
         ctx.layers[cfg.enc_blocks + l] = None
+        ready(G)
     dxe = ops.scale_dropout(dx, xscale, _drop(cfg.dec_pos_dropout, sv["s_dx"], training), out_dtype=torch.float32)
     dx, dg, db = ops.ln_bwd(dxe, sv["enc_x"], sv["enc_mean"], sv["enc_rstd"], P["encoder.after_norm.weight"],
                             P["encoder.after_norm.bias"], eps=1e-12)
@@ -510,6 +515,7 @@ def backward(ops, P, wc: WeightCache, cfg: A3TConfig, ctx: StepContext, gloss: t
         dx = _layer_bwd(ops, P, wc, f"encoder.encoders.{l}", dx, sv["pos_e"], cfg.H, cfg.dropout, cfg.att_dropout,
                         training, ctx.layers[l], G)
         ctx.layers[l] = None
+        ready(G)
 
     V = P["encoder.text_embed.0.weight"].shape[0]
     dsy, demb, dseg = ops.embed_assemble_bwd(dx, sv["text"], sv["sseg"], sv["tseg"], V, cfg.n_segments, xscale, V - 1,

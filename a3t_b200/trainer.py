@@ -1,10 +1,15 @@
-"""Data-parallel training step for the A3T model: one process per GPU, ONE NCCL all-reduce.
+"""Data-parallel training step for the A3T model: one process per GPU, one flat gradient buffer whose
+all-reduce is issued range by range as the backward sweep finishes them (overlapped with the sweep).
 
 Replaces the reference's trainer glue for this path (espnet2/train/trainer.py:243-275 DDP wrap,
 :583-597 loss weighting, :631-675 clip / Adam / Noam):
   * every parameter is a view into one flat fp32 buffer; gradients into a second flat buffer
     whose 4-float tail carries the statistics the reference all-reduces separately
-    (sum loss*B, sum loss_mlm*B, sum B, stop flag) -> a single in-place all-reduce per step;
+    (sum loss*B, sum loss_mlm*B, sum B, stop flag) -> one logical in-place all-reduce of that buffer per step,
+    cut into contiguous ranges (>= `bucket_bytes`, about one Conformer block) that are handed to NCCL as soon as
+    the backward sweep has written them: the parameter order of the flat buffer is the reverse of the order the
+    sweep finishes gradients in, so the finished region is always a suffix, and only the last range
+    (first encoder block + embeddings) is exposed after the sweep;
   * gradient = sum_r(loss_r * B_r) / sum_r B_r, as trainer.py:583-595 + DDP mean produce;
   * clip_grad_norm_(max_norm) + Adam + NoamLR fused in one kernel pass (`a3t_adam_step`), with the
     non-finite-norm skip of trainer.py:640-656 decided on the device (no host sync);
@@ -23,7 +28,7 @@ from . import _lib, graph
 class DataParallelTrainer:
     def __init__(self, model, lr: float = 1.0, warmup: float = 4000.0, model_size: Optional[float] = None,
                  betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None, ops=None,
-                 update_fn=None):
+                 update_fn=None, bucket_bytes: int = 24 << 20):
         """`ops` / `update_fn` exist for the CPU multi-process tests only (tests/test_dist_cpu.py passes the
         oracle backend and a torch restatement of `a3t_adam_step` to exercise the flat-buffer exchange
         over gloo); the product path leaves them None and requires a CUDA model."""
@@ -62,6 +67,37 @@ class DataParallelTrainer:
         self._plan, self._plan_gen, self._qkv4 = None, -1, []
         self.in_place_repack = True  # False: drop the packed-weight cache after every step (lazy per-weight re-pack)
         self._rest = None
+        self.bucket_floats = max(1, int(bucket_bytes) // 4)
+        self._offsets = [0]
+        for sz in sizes:
+            self._offsets.append(self._offsets[-1] + sz)
+        self.exchange_ranges = []  # [(lo, hi)] of the last step's all-reduce calls, in issue order
+
+    def _exchange_hook(self, works):
+        """Callback for `graph.backward(on_ready=...)`: copies the finished small gradients into the flat buffer
+        and all-reduces (async, on NCCL's own stream) the finished suffix once it is at least one bucket long."""
+        seen, state = set(), {"front": len(self.names), "hi": self.n + 4}
+        self.exchange_ranges = []
+
+        def hook(G, final=False):
+            new = [n for n in G if n not in seen]
+            cp = [n for n in new if G[n].data_ptr() != self.gviews[n].data_ptr()]
+            if cp:
+                torch._foreach_copy_([self.gviews[n] for n in cp], [G[n].view(self.gviews[n].shape) for n in cp])
+            seen.update(new)
+            i = state["front"]
+            while i > 0 and self.names[i - 1] in seen:
+                i -= 1
+            lo, hi = (0 if final else self._offsets[i]), state["hi"]
+            if final and i != 0:
+                missing = [n for n in self.names[:i] if n not in seen]
+                raise _lib.A3TError(f"backward produced no gradient for {missing[:4]}")
+            if hi > lo and (final or hi - lo >= self.bucket_floats):
+                works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                self.exchange_ranges.append((lo, hi))
+                state["front"], state["hi"] = i, lo
+
+        return hook
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """One optimizer step on this rank's shard of the global batch.  Returns the device tensor
@@ -75,17 +111,25 @@ class DataParallelTrainer:
         # one clear of the flat gradient buffer: weight-gradient GEMMs then write (split-K: accumulate) straight
         # into its views; only the small vectors (biases, norms, embeddings) are copied in afterwards
         self.flat_g.zero_()
-        G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews)
-        if self._rest is None:  # which gradients were not written in place is a property of the graph, not of the step
-            self._rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
-        rest = self._rest
-        torch._foreach_copy_([self.gviews[n] for n in rest], [G[n].view(self.gviews[n].shape) for n in rest])
         self.stats[0:1].copy_(loss).mul_(float(B))
         self.stats[1:2].copy_(loss).mul_(float(B))
         self.stats[2:3].fill_(float(B))
         self.stats[3:4].fill_(0.0)
-        if self.world > 1:  # C3 (+C5/C6 piggy-backed): the single collective of the step
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.world > 1:
+            # C3 (+C5/C6 piggy-backed): the flat buffer (statistics tail included, with the first range) is
+            # all-reduced range by range while the sweep runs; the step waits for all of them before the norm
+            works = []
+            hook = self._exchange_hook(works)
+            G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews, on_ready=hook)
+            hook(G, final=True)
+            for w in works:
+                w.wait()
+        else:
+            G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews)
+            if self._rest is None:  # which gradients were not written in place is a property of the graph
+                self._rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
+            rest = self._rest
+            torch._foreach_copy_([self.gviews[n] for n in rest], [G[n].view(self.gviews[n].shape) for n in rest])
         if self._update_fn is not None:  # CPU test seam
             self._update_fn(self)
             wc.clear()

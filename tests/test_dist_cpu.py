@@ -46,15 +46,16 @@ def _update(tr):
     tr.step_count += 1
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bucket_bytes):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     fx = torch.load(GOLDEN, weights_only=False)
     m = _model(fx)
-    tr = DataParallelTrainer(m, ops=OracleBackend(), update_fn=_update)
+    tr = DataParallelTrainer(m, ops=OracleBackend(), update_fn=_update, bucket_bytes=bucket_bytes)
     stats = tr.step(_shard(fx["batch"], rank, world)).clone()
-    torch.save({"p": tr.flat_p.clone(), "g": tr.flat_g.clone(), "stats": stats}, f"{out}.{rank}")
+    torch.save({"p": tr.flat_p.clone(), "g": tr.flat_g.clone(), "stats": stats, "ranges": tr.exchange_ranges,
+                "n": tr.n}, f"{out}.{rank}")
     dist.destroy_process_group()
 
 
@@ -67,11 +68,18 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_step_matches_weighted_single_process(tmp_path):
+@pytest.mark.parametrize("bucket_bytes", [24 << 20, 64 << 10])
+def test_two_rank_step_matches_weighted_single_process(tmp_path, bucket_bytes):
+    """bucket_bytes = 24 MiB: the tiny model fits one range (a single all-reduce); 64 KiB: the exchange is cut
+    into several ranges issued during the backward sweep -- same result, ranges tile [0, n + 4) back to front."""
     world = 2
     out = str(tmp_path / "rank")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, bucket_bytes), nprocs=world, join=True)
     r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    rg = r0["ranges"]
+    assert rg == r1["ranges"] and rg[0][1] == r0["n"] + 4 and rg[-1][0] == 0
+    assert all(a[0] == b[1] for a, b in zip(rg, rg[1:]))
+    assert (len(rg) == 1) if bucket_bytes >= (1 << 20) else (len(rg) >= 4)
     # every rank holds the same reduced gradient, statistics and updated parameters
     assert torch.equal(r0["g"], r1["g"]) and torch.equal(r0["p"], r1["p"])
     # expected: per-shard gradients computed independently, combined as sum_r(g_r * B_r) / sum_r B_r
