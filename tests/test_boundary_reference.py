@@ -137,3 +137,27 @@ def test_reference_built_model_runs_model_call_on_gpu(golden_dir, cuda_lib):
     assert abs(float(loss) - float(fx["loss_train"])) <= 2e-4 * abs(float(fx["loss_train"]))
     g = model.sfc.weight.grad.cpu()
     assert float((g - fx["grads"]["sfc.weight"]).abs().max()) <= 5e-4 * float(fx["grads"]["sfc.weight"].abs().max()) + 5e-5
+
+
+@needs_ref
+def test_reference_mlm_tts_model_forward_is_dead_code():
+    """SURVEY 8(f) rank 2 names `ESPnetMLMTTSModel` (sedit_model.py:377-557) as the next model class.  In the reference
+    as shipped its `_forward` cannot run with ANY encoder choice: it unpacks three values from `self.encoder(**batch)`
+    (sedit_model.py:419) while `MLMEncoder.forward` returns two (conformer/encoder.py:557), so the first training or
+    inference call raises ValueError.  There is therefore no reference behaviour to be a drop-in for; this test pins
+    that finding so DESIGN.md's "out of scope" entry stays checkable."""
+    R._activate()
+    import espnet2.tasks.mlm as mlm
+
+    conf = R.model_conf("cfg1")
+    args = _args(conf, vocab=20)
+    args.model_conf = dict(args.model_conf, duration_predictor_layers=2)   # selects the class at mlm.py:416-425
+    torch.manual_seed(0)
+    model = mlm.MLMTask.build_model(args)
+    assert type(model).__name__ == "ESPnetMLMTTSModel"
+    batch, _ = R.synthetic_batch(B=2, Ts=40, Tt=8, vocab=20, seed=0)
+    # identity reduction: every frame kept, duration 1 (collate_fn.py:290-328 would shorten masked spans)
+    batch["durations"] = torch.ones(2, 40, dtype=torch.long)
+    batch["reordered_index"] = torch.arange(40).unsqueeze(0).repeat(2, 1)
+    with pytest.raises(ValueError, match="not enough values to unpack"):
+        model(**batch)
