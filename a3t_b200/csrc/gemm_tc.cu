@@ -39,6 +39,9 @@ constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
 constexpr int SMEM_BYTES_MAX = 227 * 1024;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int MAX_STAGES = 8;
+constexpr int CLC_SLOTS = 4;   // ring of cluster-launch-control responses (work items fetched ahead)
+constexpr int NUM_BARS = 2 * MAX_STAGES + 5 + NUM_EPI_WARPS + 3 * CLC_SLOTS;
+constexpr int BAR_BYTES = ((8 * NUM_BARS + 15) / 16) * 16 + 16 * CLC_SLOTS + 16;
 
 struct Params {
   A3tGemmDesc d;
@@ -64,6 +67,8 @@ struct Params {
   int num_work;         // m_tiles * n_tiles * batch * splits
   int a_c2, a_c3, b_c2, b_c3;  // 0 when that batch coordinate is pinned (stride 0 / size 1)
   int vec_c, vec_r, vec_m;     // 16-byte vector access allowed for C / residual / mask
+  int clc;                     // 1 = dynamic tile order through cluster launch control (grid = one CTA / pair per work item,
+                               // running CTAs cancel pending ones and take over their index); 0 = static round robin
   int dbg;                     // tuning experiments: 1 = no loads, MMAs free-run; 2 = loads run, MMAs do not wait; 3 = loads only; 5 = loads only, no epilogue; 6 = no epilogue (timing only, garbage results)
 };
 
@@ -244,6 +249,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
   auto res_bar = [&](int w) { return bar_base + 8u * (2 * MAX_STAGES + 5 + w); };  // one per epilogue warp
+  // cluster launch control: response ring + full (response landed) / empty (consumers done) / armed (pair mode: the
+  // peer CTA has armed its own full barrier, the leader may multicast the next response) barriers
+  constexpr int CLC_BAR0 = 2 * MAX_STAGES + 5 + NUM_EPI_WARPS;
+  auto clc_full = [&](int s) { return bar_base + 8u * (CLC_BAR0 + s); };
+  auto clc_empty = [&](int s) { return bar_base + 8u * (CLC_BAR0 + CLC_SLOTS + s); };
+  auto clc_armed = [&](int s) { return bar_base + 8u * (CLC_BAR0 + 2 * CLC_SLOTS + s); };
+  const uint32_t clc_resp = bar_base + ((8u * NUM_BARS + 15u) & ~15u);
+  const bool clc = p.clc != 0;
+  // next work item of this role.  Static order: stride ngroups.  CLC: wait for the response of query #it (issued by
+  // the producer thread one item ahead), release the slot (MMA thread: arrive; epilogue warps: lane 0 after a warp
+  // sync; the producer threads do not arrive -- they are the ones waiting on `empty`).
+  auto next_work = [&](int& w, int& it, int who) -> bool {   // who: 0 = producer, 1 = single thread, 2 = whole warp
+    if (!clc) {
+      w += ngroups;
+      return w < p.num_work;
+    }
+    const int slot = it & (CLC_SLOTS - 1);
+    mbar_wait(clc_full(slot), (uint32_t)(it / CLC_SLOTS) & 1u);
+    uint32_t x;
+    const bool ok = clc_read(clc_resp + 16u * slot, x);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot is rewritten through the async proxy
+    if (who == 1) mbar_arrive(clc_empty(slot));
+    if (who == 2) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(clc_empty(slot));
+    }
+    it++;
+    w = (int)(CTA2 ? (x >> 1) : x);
+    return ok;
+  };
 
   if (warp == PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -259,6 +294,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tempty_bar(a), NUM_EPI_WARPS * per_unit);  // pair mode: the peer's epilogue warps arrive remotely
     }
     for (int w = 0; w < NUM_EPI_WARPS; w++) mbar_init(res_bar(w), 1);
+    for (int s = 0; s < CLC_SLOTS; s++) {
+      mbar_init(clc_full(s), 1);
+      mbar_init(clc_empty(s), NUM_EPI_WARPS + (rank == 0 ? 1 : 0));  // epilogue warps (+ the MMA thread on the leader)
+      mbar_init(clc_armed(s), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -314,7 +354,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         dj[0] = p.a_mn ? 0 : BLOCK_K; dj[1] = p.a_mn ? BLOCK_K : 0;
         dj[4] = p.b_mn ? 0 : BLOCK_K; dj[5] = p.b_mn ? BLOCK_K : 0;
       }
-      for (int w = group; w < p.num_work; w += ngroups) {
+      int w = group, wit = 0;
+      for (;;) {
+        if (clc) {
+          // query #wit (answers: which item follows this one) goes out before this item's loads
+          const int slot = wit & (CLC_SLOTS - 1);
+          const uint32_t sph = (uint32_t)(wit / CLC_SLOTS) & 1u;
+          mbar_wait(clc_empty(slot), sph ^ 1u);
+          mbar_expect_tx(clc_full(slot), 16);
+          if constexpr (CTA2) {
+            if (rank != 0) {
+              mbar_arrive_leader(clc_armed(slot));
+            } else {
+              mbar_wait(clc_armed(slot), sph);
+              clc_try_cancel_multicast(clc_resp + 16u * slot, clc_full(slot));
+            }
+          } else {
+            clc_try_cancel(clc_resp + 16u * slot, clc_full(slot));
+          }
+        }
         const Work t = decode_work(p, w, (int)rank, per_unit);
         int o0 = 0, j = t.k_begin;
         if (inner != p.k_iters) { o0 = t.k_begin / inner; j = t.k_begin - o0 * inner; }
@@ -363,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 8; i++) c[i] += dw[i];
           }
         }
+        if (!next_work(w, wit, 0)) break;
       }
     }
   } else if (warp == MMA_WARP) {
@@ -380,7 +439,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stage16 = stage_bytes >> 4;
       const bool wait_full = dbg != 1 && dbg != 2, do_mma = dbg != 3 && dbg != 5;
       const uint32_t idesc = p.idesc;
-      for (int w = group; w < p.num_work; w += ngroups) {
+      int w = group, wit = 0;
+      for (;;) {
         const Work t = decode_work(p, w, 0, per_unit);
         mbar_wait(tempty_bar(as), aph ^ 1);
         tc_fence_after();
@@ -407,6 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CTA2) umma_commit_2sm(tfull_bar(as));
         else umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aph ^= 1; }
+        if (!next_work(w, wit, 1)) break;
       }
     }
   } else {
@@ -433,7 +494,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stg_row = stg + lane * 128;
       const uint32_t sw = (uint32_t)(lane & 7);
       const int nch = (dbg >= 5) ? 0 : (p.wg_alltaps ? 6 : (p.block_n + 31) / 32);
-      for (int w = group; w < p.num_work; w += ngroups) {
+      int w = group, wit = 0;
+      for (;;) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
         const int trow0 = t.m0 + q * 32;
         const uint32_t taddr_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
@@ -492,6 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
+        if (!next_work(w, wit, 2)) break;
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else
@@ -500,7 +563,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float alpha = d.alpha;
       const bool atomic = p.splits > 1;
       float* const Cf = (float*)p.C;
-      for (int w = group; w < p.num_work; w += ngroups) {
+      int w = group, wit = 0;
+      for (;;) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
         const int row0 = t.m0 + q * 32 + rsub;
         bool waited = false, released = false;
@@ -560,6 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
+        if (!next_work(w, wit, 2)) break;
       }
     } else
     if constexpr (EPI >= 0) {
@@ -580,7 +645,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stg_row = stg + lane * 128;
       const uint32_t sw = (uint32_t)(lane & 7);
       uint32_t rph = 0;  // phase of this warp's residual barrier
-      for (int w = group; w < p.num_work; w += ngroups) {
+      int w = group, wit = 0;
+      for (;;) {
         const Work t = decode_work(p, w, (int)rank, per_unit);
         const int trow0 = t.m0 + q * 32;                              // first row of this warp (in sequence / matrix)
         const int row = trow0 + lane;
@@ -710,10 +776,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
+        if (!next_work(w, wit, 2)) break;
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
-    } else
-    for (int w = group; w < p.num_work; w += ngroups) {
+    } else {
+    int w = group, wit = 0;
+    for (;;) {
       const Work t = decode_work(p, w, (int)rank, per_unit);
       const int64_t cbase = (int64_t)t.b1 * d.sc_b1 + (int64_t)t.b2 * d.sc_b2;
       const int64_t rbase = (int64_t)t.b1 * d.sr_b1 + (int64_t)t.b2 * d.sr_b2;
@@ -770,6 +838,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
+      if (!next_work(w, wit, 2)) break;
+    }
     }
   }
 
@@ -952,7 +1022,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   abox[1] = p.a_mn ? BLOCK_K : BLOCK_M;
   bbox[1] = p.b_mn ? BLOCK_K : b_rows;
   const uint32_t stage_bytes = A_STAGE_BYTES + b_rows * BLOCK_K * 2;
-  const int bar_bytes = 8 * (2 * MAX_STAGES + 5 + NUM_EPI_WARPS) + 16;
+  const int bar_bytes = BAR_BYTES;
   const int epi_bytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
   p.stages = (SMEM_BYTES_MAX - 1024 - bar_bytes - epi_bytes) / (int)stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -1046,6 +1116,11 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     }
   }
   if (const char* e = tune_env("A3T_TC_DBGMODE")) p.dbg = atoi(e);
+  // dynamic tile order (cluster launch control): the grid is one CTA (pair) per work item, the hardware launches as
+  // many as fit and every running CTA cancels pending ones to take over their index.  Unlike a persistent grid of
+  // exactly #SM CTAs this keeps its speed when another kernel (the NCCL all-reduce of finished gradient ranges)
+  // occupies some SMs: no CTA waits a whole kernel duration for an SM.
+  p.clc = (p.dbg == 0 && !tune_env("A3T_TC_STATIC")) ? 1 : 0;
   if (tune_env("A3T_TC_DEBUG"))
     fprintf(stderr, "gemm_tc: M=%d N=%d K=%d mode=%d cta2=%d bn=%d splits=%d stages=%d work=%d epi=%d\n", d.M, d.N, d.K,
             d.mode, (int)cta2, p.block_n, p.splits, p.stages, p.num_work, epi);
@@ -1055,7 +1130,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
   int nattr = 0;
   if (cta2) {
     int groups = sms / 2;
-    int g = p.num_work < groups ? p.num_work : groups;
+    int g = (p.clc || p.num_work < groups) ? p.num_work : groups;
     cfg.gridDim = dim3(2 * g);
     attr[nattr].id = cudaLaunchAttributeClusterDimension;
     attr[nattr].val.clusterDim.x = 2;
@@ -1063,7 +1138,7 @@ int gemm_tc_launch(const A3tGemmDesc* dp, const void* A, const void* B, void* C,
     attr[nattr].val.clusterDim.z = 1;
     nattr++;
   } else {
-    cfg.gridDim = dim3(p.num_work < sms ? p.num_work : sms);
+    cfg.gridDim = dim3((p.clc || p.num_work < sms) ? p.num_work : sms);
   }
   static const bool pdl = !tune_env("A3T_NO_PDL");
   if (pdl && !(p.splits > 1 && !d.c_zeroed)) {  // (the library's own memset node must not be overtaken)

@@ -60,6 +60,37 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap*
       "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// ---- cluster launch control (sm_100): a running CTA cancels a not-yet-launched CTA (cluster) of its own grid and
+// takes over its index.  The 16-byte response lands in shared memory through the async proxy and completes 16 tx
+// bytes on the mbarrier; the multicast form writes it (and signals the barrier) at the same offsets in every CTA of
+// the cluster.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(resp),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp, uint32_t bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::"r"(
+          resp),
+      "r"(bar)
+      : "memory");
+}
+// true + blockIdx.x of the cancelled CTA (first CTA of the cancelled cluster) when the request succeeded
+__device__ __forceinline__ bool clc_read(uint32_t resp, uint32_t& ctaid_x) {
+  uint32_t valid, x = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+      : "+r"(x), "=r"(valid)
+      : "r"(resp)
+      : "memory");
+  ctaid_x = x;
+  return valid != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

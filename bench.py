@@ -466,6 +466,8 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of untimed back-to-back steps before the timed region")
     ap.add_argument("--bucket-mb", type=float, default=24.0,
                     help="N>1: minimum size of a gradient range handed to NCCL during the backward sweep (huge = one all-reduce after it)")
+    ap.add_argument("--diag-no-exchange", action="store_true",
+                    help="diagnostic, N>1: run the ranks side by side WITHOUT the gradient all-reduce (not a valid bench line)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the frontend / vocoder side measurements")
@@ -501,6 +503,8 @@ def main():
             if p.dim() == 1 and n.endswith("weight"):
                 p.fill_(1.0)
     trainer = DataParallelTrainer(model, bucket_bytes=int(args.bucket_mb * (1 << 20)))
+    if args.diag_no_exchange:
+        trainer.world = 1
     B, Ts, Tt = args.batch, args.frames, args.phones
     host = synthetic_batch_host(B, Ts, Tt, seed=rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
@@ -624,7 +628,7 @@ def main():
             "config": {"workload": f"{args.config}: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
                                    f"B={B}/GPU, Ts={Ts}, Tt={Tt}, train step fwd+bwd+allreduce+clip/Adam/Noam, dropout on",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": used_graph,
-                       "graph_error": graph_err,
+                       "graph_error": graph_err, **({"diag": "NO gradient exchange (diagnostic run)"} if args.diag_no_exchange else {}),
                        "grad_exchange_ranges": len(trainer.exchange_ranges) if world > 1 else 0, "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                        "loss": loss_now, "alg_tflop_per_step_per_gpu": alg_flops_step / 1e12,
                        "step_tensor_frac_of_peak": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / peak},
