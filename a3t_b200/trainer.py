@@ -1,15 +1,18 @@
-"""Data-parallel training step for the A3T model: one process per GPU, one flat gradient buffer whose
-all-reduce is issued range by range as the backward sweep finishes them (overlapped with the sweep).
+"""Data-parallel training step for the A3T model: one process per GPU, ONE all-reduce of one flat gradient buffer
+(optionally issued range by range while the backward sweep is still running, `bucket_bytes > 0`).
 
 Replaces the reference's trainer glue for this path (espnet2/train/trainer.py:243-275 DDP wrap,
 :583-597 loss weighting, :631-675 clip / Adam / Noam):
   * every parameter is a view into one flat fp32 buffer; gradients into a second flat buffer
     whose 4-float tail carries the statistics the reference all-reduces separately
-    (sum loss*B, sum loss_mlm*B, sum B, stop flag) -> one logical in-place all-reduce of that buffer per step,
-    cut into contiguous ranges (>= `bucket_bytes`, about one Conformer block) that are handed to NCCL as soon as
-    the backward sweep has written them: the parameter order of the flat buffer is the reverse of the order the
-    sweep finishes gradients in, so the finished region is always a suffix, and only the last range
-    (first encoder block + embeddings) is exposed after the sweep;
+    (sum loss*B, sum loss_mlm*B, sum B, stop flag) -> a single in-place all-reduce per step (default).
+    With `bucket_bytes > 0` the same buffer is cut into contiguous ranges of at least that size that are handed to
+    NCCL (async, high-priority communicator of its own) as soon as the backward sweep has written them: the
+    parameter order of the flat buffer is the reverse of the order the sweep finishes gradients in, so the finished
+    region is always a suffix.  Measured on 8 x B200 (profiles/r02_scaling_overlap.md): NCCL's all-reduce kernels
+    overlap the sweep but take 16-24 SMs, which costs the co-running tcgen05 GEMMs as much as the overlap hides
+    (a 144-tile GEMM needs two waves on 124 SMs); with max_ctas = 4 nothing is disturbed but the last range is
+    then exposed for 0.5 ms.  Net gain: +1 % at 2 GPUs, none at 8 -- hence opt-in;
   * gradient = sum_r(loss_r * B_r) / sum_r B_r, as trainer.py:583-595 + DDP mean produce;
   * clip_grad_norm_(max_norm) + Adam + NoamLR fused in one kernel pass (`a3t_adam_step`), with the
     non-finite-norm skip of trainer.py:640-656 decided on the device (no host sync);
@@ -28,13 +31,14 @@ from . import _lib, graph
 class DataParallelTrainer:
     def __init__(self, model, lr: float = 1.0, warmup: float = 4000.0, model_size: Optional[float] = None,
                  betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None, ops=None,
-                 update_fn=None, bucket_bytes: int = 24 << 20):
+                 update_fn=None, bucket_bytes: int = 0, exchange_max_ctas: int = 0):
         """`ops` / `update_fn` exist for the CPU multi-process tests only (tests/test_dist_cpu.py passes the
         oracle backend and a torch restatement of `a3t_adam_step` to exercise the flat-buffer exchange
         over gloo); the product path leaves them None and requires a CUDA model."""
         self.model = model
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.xpg = process_group  # group the gradient ranges are exchanged on
         self.lr, self.warmup, self.betas, self.eps, self.max_norm = lr, warmup, betas, eps, max_norm
         self.model_size = float(model_size if model_size is not None else model.encoder.attention_dim)
         params = [(n, p) for n, p in model.named_parameters()]
@@ -58,6 +62,15 @@ class DataParallelTrainer:
             off += sz
         if self.world > 1:  # C2: one parameter broadcast at init (trainer.py:250-265)
             dist.broadcast(self.flat_p, 0, group=self.pg)
+            if bucket_bytes > 0 and dev.type == "cuda" and dist.get_backend(self.pg) == "nccl":
+                # the range all-reduces run beside the backward kernels: on a HIGH-priority stream their CTAs are
+                # placed as soon as any SM frees up (the default NCCL stream has normal priority and would queue
+                # behind every already-launched compute kernel -- measured: no overlap at all at 8 GPUs)
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                if exchange_max_ctas:
+                    opts.config.max_ctas = int(exchange_max_ctas)
+                ranks = dist.get_process_group_ranks(self.pg) if self.pg is not None else list(range(self.world))
+                self.xpg = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.sq_partial = torch.zeros(1024, dtype=torch.float64, device=dev)
@@ -67,7 +80,7 @@ class DataParallelTrainer:
         self._plan, self._plan_gen, self._qkv4 = None, -1, []
         self.in_place_repack = True  # False: drop the packed-weight cache after every step (lazy per-weight re-pack)
         self._rest = None
-        self.bucket_floats = max(1, int(bucket_bytes) // 4)
+        self.bucket_floats = int(bucket_bytes) // 4  # 0 = one all-reduce after the sweep
         self._offsets = [0]
         for sz in sizes:
             self._offsets.append(self._offsets[-1] + sz)
@@ -93,7 +106,7 @@ class DataParallelTrainer:
                 missing = [n for n in self.names[:i] if n not in seen]
                 raise _lib.A3TError(f"backward produced no gradient for {missing[:4]}")
             if hi > lo and (final or hi - lo >= self.bucket_floats):
-                works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.xpg, async_op=True))
                 self.exchange_ranges.append((lo, hi))
                 state["front"], state["hi"] = i, lo
 
@@ -115,9 +128,9 @@ class DataParallelTrainer:
         self.stats[1:2].copy_(loss).mul_(float(B))
         self.stats[2:3].fill_(float(B))
         self.stats[3:4].fill_(0.0)
-        if self.world > 1:
-            # C3 (+C5/C6 piggy-backed): the flat buffer (statistics tail included, with the first range) is
-            # all-reduced range by range while the sweep runs; the step waits for all of them before the norm
+        if self.world > 1 and self.bucket_floats > 0:
+            # C3 (+C5/C6 piggy-backed), overlapped variant: the flat buffer (statistics tail included, with the first
+            # range) is all-reduced range by range while the sweep runs; the step waits for all before the norm
             works = []
             hook = self._exchange_hook(works)
             G = graph.backward(ops, P, wc, cfg, ctx, gloss, gout=self.gviews, on_ready=hook)
@@ -130,6 +143,9 @@ class DataParallelTrainer:
                 self._rest = [n for n in self.names if G[n].data_ptr() != self.gviews[n].data_ptr()]
             rest = self._rest
             torch._foreach_copy_([self.gviews[n] for n in rest], [G[n].view(self.gviews[n].shape) for n in rest])
+            if self.world > 1:  # C3 (+C5/C6 piggy-backed): the single collective of the step
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                self.exchange_ranges = [(0, self.n + 4)]
         if self._update_fn is not None:  # CPU test seam
             self._update_fn(self)
             wc.clear()

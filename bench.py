@@ -464,10 +464,16 @@ def main():
                          "cfg5: batched infill + vocoder inference (own metric)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of untimed back-to-back steps before the timed region")
-    ap.add_argument("--bucket-mb", type=float, default=24.0,
-                    help="N>1: minimum size of a gradient range handed to NCCL during the backward sweep (huge = one all-reduce after it)")
+    ap.add_argument("--bucket-mb", type=float, default=0.0,
+                    help="N>1: 0 = one all-reduce after the backward sweep (default); > 0 = minimum size of the gradient ranges "
+                         "handed to NCCL while the sweep is still running (profiles/r02_scaling_overlap.md)")
     ap.add_argument("--diag-no-exchange", action="store_true",
                     help="diagnostic, N>1: run the ranks side by side WITHOUT the gradient all-reduce (not a valid bench line)")
+    ap.add_argument("--diag-tiny-exchange", action="store_true",
+                    help="diagnostic, N>1: no gradient exchange but a 16-byte all-reduce per step (cost of lock step alone)")
+    ap.add_argument("--exchange-ctas", type=int, default=0, help="N>1: NCCL max_ctas of the gradient-exchange communicator (0 = NCCL default)")
+    ap.add_argument("--kernel-trace", default=None,
+                    help="after the timed region: CUPTI kernel timeline (name, start, duration, stream, grid) of 2 steps on rank 0 -> CSV")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the frontend / vocoder side measurements")
@@ -502,9 +508,18 @@ def main():
         for n, p in model.named_parameters():
             if p.dim() == 1 and n.endswith("weight"):
                 p.fill_(1.0)
-    trainer = DataParallelTrainer(model, bucket_bytes=int(args.bucket_mb * (1 << 20)))
-    if args.diag_no_exchange:
+    trainer = DataParallelTrainer(model, bucket_bytes=int(args.bucket_mb * (1 << 20)), exchange_max_ctas=args.exchange_ctas)
+    if args.diag_no_exchange or args.diag_tiny_exchange:
         trainer.world = 1
+    if args.diag_tiny_exchange:  # gradients stay local; one 16-byte all-reduce per step keeps the ranks in lock step
+        _step = trainer.step
+
+        def _step_sync(b):
+            r = _step(b)
+            dist.all_reduce(trainer.stats)
+            return r
+
+        trainer.step = _step_sync
     B, Ts, Tt = args.batch, args.frames, args.phones
     host = synthetic_batch_host(B, Ts, Tt, seed=rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
@@ -573,6 +588,32 @@ def main():
     frames = world * B * Ts * args.steps
     value = frames / (ms / 1e3)
 
+    if args.kernel_trace:  # diagnostic: do the collectives overlap the backward kernels?
+        barrier()
+        if rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(2):
+                    one_step()
+                torch.cuda.synchronize()
+            tmp = args.kernel_trace + ".json"
+            prof.export_chrome_trace(tmp)
+            ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+            ev.sort(key=lambda e: e["ts"])
+            t0 = ev[0]["ts"] if ev else 0
+            with open(args.kernel_trace, "w") as f:
+                f.write("start_us,dur_us,stream,grid,block,name\n")
+                for e in ev:
+                    a = e.get("args", {})
+                    f.write(f"{e['ts'] - t0:.3f},{e['dur']:.3f},{a.get('stream')},\"{a.get('grid')}\",\"{a.get('block')}\",\"{e['name'][:90]}\"\n")
+            os.remove(tmp)
+        else:
+            for _ in range(2):
+                one_step()
+            torch.cuda.synchronize()
+        barrier()
+
     # ---- e2e: host (pinned) buffers in, loss out, through the public trainer API ---------------
     barrier()
     e0.record()
@@ -628,7 +669,7 @@ def main():
             "config": {"workload": f"{args.config}: VCTK paper Conformer (4+4 blocks, D=384, H=2, FF=1536 k3, dw 7/31, postnet 5x256), "
                                    f"B={B}/GPU, Ts={Ts}, Tt={Tt}, train step fwd+bwd+allreduce+clip/Adam/Noam, dropout on",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": used_graph,
-                       "graph_error": graph_err, **({"diag": "NO gradient exchange (diagnostic run)"} if args.diag_no_exchange else {}),
+                       "graph_error": graph_err, **({"diag": "NO gradient exchange (diagnostic run)"} if (args.diag_no_exchange or args.diag_tiny_exchange) else {}),
                        "grad_exchange_ranges": len(trainer.exchange_ranges) if world > 1 else 0, "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                        "loss": loss_now, "alg_tflop_per_step_per_gpu": alg_flops_step / 1e12,
                        "step_tensor_frac_of_peak": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / peak},

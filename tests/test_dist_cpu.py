@@ -68,10 +68,11 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("bucket_bytes", [24 << 20, 64 << 10])
+@pytest.mark.parametrize("bucket_bytes", [0, 24 << 20, 64 << 10])
 def test_two_rank_step_matches_weighted_single_process(tmp_path, bucket_bytes):
-    """bucket_bytes = 24 MiB: the tiny model fits one range (a single all-reduce); 64 KiB: the exchange is cut
-    into several ranges issued during the backward sweep -- same result, ranges tile [0, n + 4) back to front."""
+    """bucket_bytes = 0 (default): one all-reduce after the backward sweep; 24 MiB: the overlapped code path, the tiny
+    model fits one range; 64 KiB: the exchange is cut into several ranges issued during the sweep -- same result,
+    ranges tile [0, n + 4) back to front."""
     world = 2
     out = str(tmp_path / "rank")
     mp.spawn(_worker, args=(world, _free_port(), out, bucket_bytes), nprocs=world, join=True)
@@ -79,7 +80,7 @@ def test_two_rank_step_matches_weighted_single_process(tmp_path, bucket_bytes):
     rg = r0["ranges"]
     assert rg == r1["ranges"] and rg[0][1] == r0["n"] + 4 and rg[-1][0] == 0
     assert all(a[0] == b[1] for a, b in zip(rg, rg[1:]))
-    assert (len(rg) == 1) if bucket_bytes >= (1 << 20) else (len(rg) >= 4)
+    assert (len(rg) == 1) if (bucket_bytes == 0 or bucket_bytes >= (1 << 20)) else (len(rg) >= 4)
     # every rank holds the same reduced gradient, statistics and updated parameters
     assert torch.equal(r0["g"], r1["g"]) and torch.equal(r0["p"], r1["p"])
     # expected: per-shard gradients computed independently, combined as sum_r(g_r * B_r) / sum_r B_r
