@@ -12,9 +12,11 @@
 //
 // BD_raw = (q+v) p^T is produced by the batched GEMM (gemm_tc.cu) in bf16 and consumed here through
 // rel_shift's index map (attention.py:145-165): BD[i,j] = BD_raw[i, S-1-i+j] (j <= i), 0 (j = i+1),
-// BD_raw[i+1, j-i-2] (j >= i+2).  Rows shift by one element per query, so the tile is loaded with lanes along
-// the key axis (coalesced 2-byte loads, any alignment) and transposed to the thread-per-query layout of
-// tcgen05.ld through a small per-warp shared-memory buffer; the backward scatters dBD_raw the same way.
+// BD_raw[i+1, j-i-2] (j >= i+2).  The band a score tile needs is a parallelogram (one element of skew per query):
+// it arrives by TMA as eight boxes of 16 query rows x (tile width + 24) columns (a TMA box must start 16-byte
+// aligned in the innermost dimension, so each box starts up to 7 elements early), and the thread that owns a query
+// (the tcgen05.ld layout) re-aligns its row window with a funnel shift.  The backward writes dS tiles by TMA tensor
+// store and scatters dBD_raw through the inverse map from the staged tile.
 //
 // Replaces: attention.py:190-209 (matmul / rel_shift / softmax / dropout / matmul) and its autograd backward.
 #include <float.h>
