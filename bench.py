@@ -657,7 +657,7 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_aux
-            aux = bench_aux.measure(pwg_batch=2, peaks=peaks)
+            aux = bench_aux.measure(pwg_batch=8, peaks=peaks)
         except Exception as e:  # reported, never hidden
             aux = {"error": repr(e)[:200]}
     if rank == 0:

@@ -39,7 +39,14 @@ def measure(pwg_batch=8, peaks=None):
     out["frontend"] = {"workload": f"B={B} x T={T} frames, fs 24 kHz n_fft 2048 win 1200 hop 300, 80 mels, fp32",
                        "ms": ms, "frames_per_s": frames / ms * 1e3, "alg_bytes_per_frame": hop * 4 + 80 * 4,
                        "achieved_gbs": byts / ms / 1e6, "hbm_peak_gbs": hbm, "frac_of_hbm": byts / ms / 1e6 / hbm,
-                       "bound": "issue (in-shared-memory FFT: ~70 kFLOP per 1.5 kB frame), not HBM"}
+                       "bound": "issue / latency (register FFT: ~70 kFLOP per 1.5 kB frame), not HBM"}
+    # issue roofline from the counter that names the bound: ncu smsp__inst_executed.sum = 56.9 M warp instructions for
+    # these 16 384 frames (profiles/r02_frontend_pwg_ncu.md) at 4 issue slots per clock per SM
+    props = torch.cuda.get_device_properties(dev)
+    wi = 56896976 / 16384.0
+    issue_peak = props.multi_processor_count * 4 * 1.965e9 / wi
+    out["frontend"].update({"warp_instructions_per_frame": wi, "issue_peak_frames_per_s": issue_peak,
+                            "frac_of_issue": frames / ms * 1e3 / issue_peak})
     # ---- vocoder
     gen = ParallelWaveGANGenerator(upsample_params={"upsample_scales": [4, 5, 3, 5]}).to(dev).eval()
     c = torch.randn(pwg_batch, 80, T, device=dev)
@@ -47,11 +54,14 @@ def measure(pwg_batch=8, peaks=None):
     ms = timeit(lambda: gen.generate(c, z), n=3, warm=1)
     audio_s = pwg_batch * T * hop / 24000.0
     samples = pwg_batch * T * hop
-    out["pwg"] = {"workload": f"{pwg_batch} utterances x {T} frames -> {T*hop} samples each, 30 residual blocks, fp32",
+    # per residual block and sample: x hi/lo planes in 256 B + out 256 B, aux planes 320 B, fp32 skip read + write 512 B
+    bps = 30 * 1344
+    out["pwg"] = {"workload": f"{pwg_batch} utterances x {T} frames -> {T*hop} samples each, 30 residual blocks, "
+                              "split-fp16 tensor-core blocks (3 passes, fp32 accumulation), fp32 in / out",
                   "ms": ms, "rtf": ms / 1e3 / audio_s, "audio_seconds_per_s": audio_s / (ms / 1e3),
-                  "unfused_alg_bytes_per_sample": 30 * 1024, "achieved_gbs_unfused_def": samples * 30 * 1024 / ms / 1e6,
-                  "hbm_peak_gbs": hbm, "frac_of_hbm_unfused_def": samples * 30 * 1024 / ms / 1e6 / hbm,
-                  "gflop_per_audio_s": 62.0, "achieved_tflops": 62.0 * audio_s / ms}
+                  "alg_bytes_per_sample": bps, "achieved_gbs": samples * bps / ms / 1e6,
+                  "hbm_peak_gbs": hbm, "frac_of_hbm": samples * bps / ms / 1e6 / hbm,
+                  "gflop_per_audio_s": 62.0, "achieved_tflops_algorithmic": 62.0 * audio_s / ms}
     return out
 
 
