@@ -70,7 +70,6 @@ class CudaBackend:
             raise _lib.A3TError("a3t_b200 runs on CUDA devices only (no CPU fallback)")
         self.act_dtype = act_dtype
         self.impl = impl if act_dtype == torch.bfloat16 else _lib.IMPL_SIMT
-        self.attn_gemm_impl = None   # override of the GEMM dispatch for the batched attention contractions (experiments)
         self.seed = torch.tensor([seed], dtype=torch.int64, device=self.device)
         # zero-initialised fp32 arena for the small outputs kernels ACCUMULATE into with atomics (bias / LayerNorm
         # parameter gradients): one memset per backward pass instead of a second reduction kernel per output.
@@ -138,8 +137,6 @@ class CudaBackend:
 
     def _gemm(self, d: GemmDesc, A, B, Cout, bias=None, res=None, mask=None, a_off=0, b_off=0, c_off=0):
         d.impl = self.impl
-        if self.attn_gemm_impl is not None and d.batch1 * d.batch2 > 1:
-            d.impl = self.attn_gemm_impl
         call("a3t_gemm", d, A.data_ptr() + a_off * A.element_size(), B.data_ptr() + b_off * B.element_size(),
              Cout.data_ptr() + c_off * Cout.element_size(), _p(bias), _p(res), _p(mask),
              _p(self.seed) if d.drop_p > 0 else None, _stream(Cout))

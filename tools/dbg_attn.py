@@ -1,5 +1,5 @@
 import math, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from a3t_b200 import _lib
 from a3t_b200.backend import CudaBackend
 B, H, S, dk = [int(x) for x in sys.argv[1:5]] if len(sys.argv) > 4 else (1, 1, 128, 64)

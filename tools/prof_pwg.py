@@ -1,5 +1,5 @@
 import collections, re, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from a3t_b200.vocoder import ParallelWaveGANGenerator
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 gen = ParallelWaveGANGenerator(upsample_params={"upsample_scales": [4, 5, 3, 5]}).cuda().eval()

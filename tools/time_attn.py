@@ -1,6 +1,6 @@
 """Times the fused attention kernels alone (CUDA events, warm) at a given shape: usage time_attn.py B H S dk [drop]"""
 import math, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from a3t_b200 import _lib
 from a3t_b200.backend import CudaBackend
 B, H, S, dk = [int(x) for x in sys.argv[1:5]] if len(sys.argv) > 4 else (16, 2, 1152, 192)

@@ -1,13 +1,13 @@
 """Times backend.attn_fwd_fused / attn_bwd_fused (fused kernel + the remaining batched GEMMs) at cfg2 shape."""
 import math, sys, torch
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from a3t_b200 import _lib
 from a3t_b200.backend import CudaBackend
 B, H, S, dk = 16, 2, 1152, 192
 D = H * dk
-impl = int(sys.argv[1]) if len(sys.argv) > 1 else _lib.IMPL_TC
-tc = CudaBackend("cuda:0", torch.bfloat16, seed=1, impl=_lib.IMPL_TC)
-tc.attn_gemm_impl = impl
+impl = int(sys.argv[1]) if len(sys.argv) > 1 else _lib.IMPL_TC   # IMPL_TC_PAIR (3): CTA pairs for every GEMM (measured slower)
+tc = CudaBackend("cuda:0", torch.bfloat16, seed=1, impl=impl)
 g = torch.Generator().manual_seed(0)
 qkv4 = torch.randn(B, S, 4 * D, generator=g).to(torch.bfloat16).cuda()
 p = torch.randn(S, D, generator=g).to(torch.bfloat16).cuda()

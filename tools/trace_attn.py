@@ -1,6 +1,6 @@
 """Per-tile timeline of CTA 0 of the fused attention kernels (needs a library built with `make TUNING=1`)."""
 import math, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from a3t_b200 import _lib
 from a3t_b200.backend import CudaBackend
 B, H, S, dk = 16, 2, 1152, 192
