@@ -661,7 +661,9 @@ def main():
         except Exception as e:  # reported, never hidden
             aux = {"error": repr(e)[:200]}
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline_leg(args)
+        # the CPU baseline is a property of the box, not of N: measured at N = 1 only (with other ranks alive their
+        # NCCL / barrier threads share the cores and the number is noise)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_leg(args)
         out = {
             "metric": f"mel-frames/sec training (VCTK A3T Conformer {args.config})", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
