@@ -4,9 +4,11 @@
 //     fill — the OOB fill is what implements the 1-D conv "same" padding and ragged edges),
 //   * fp32 accumulators in TMEM (2 x 256 columns, double buffered against the epilogue),
 //   * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, cta_group::1),
-//   * warp-specialised persistent CTAs (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer and
-//     TMEM owner, warps 2..9 = epilogue (tcgen05.ld -> smem transpose -> bias/ReLU/mask/dropout/
-//     residual -> coalesced global stores).
+//   * warp-specialised CTAs (1 per SM) that keep taking work items until none is left: warps 0..7 = epilogue
+//     (tcgen05.ld -> bias / ReLU / mask / dropout / residual in registers -> swizzled staging rows -> TMA tensor
+//     store), warp 8 = TMA producer, warp 9 = MMA issuer and TMEM owner.  The order of work items is dynamic:
+//     cluster launch control (the grid is one CTA or CTA pair per item, running CTAs cancel pending ones and take
+//     over their index), so the kernel uses whatever SMs are free when another kernel holds some.
 //
 // Modes (include/a3t_b200.h): PLAIN (any of the four operand-major combinations, batched),
 // CONV (implicit 1-D conv: K loop over (tap, channel block), A rows shifted by tap - pad inside
