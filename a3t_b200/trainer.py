@@ -31,7 +31,7 @@ from . import _lib, graph
 class DataParallelTrainer:
     def __init__(self, model, lr: float = 1.0, warmup: float = 4000.0, model_size: Optional[float] = None,
                  betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, process_group=None, ops=None,
-                 update_fn=None, bucket_bytes: int = 0, exchange_max_ctas: int = 0):
+                 update_fn=None, bucket_bytes: int = 0, exchange_max_ctas: int = 0, last_range_full_speed: bool = False):
         """`ops` / `update_fn` exist for the CPU multi-process tests only (tests/test_dist_cpu.py passes the
         oracle backend and a torch restatement of `a3t_adam_step` to exercise the flat-buffer exchange
         over gloo); the product path leaves them None and requires a CUDA model."""
@@ -39,6 +39,7 @@ class DataParallelTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.xpg = process_group  # group the gradient ranges are exchanged on
+        self.last_range_full_speed = bool(last_range_full_speed)
         self.lr, self.warmup, self.betas, self.eps, self.max_norm = lr, warmup, betas, eps, max_norm
         self.model_size = float(model_size if model_size is not None else model.encoder.attention_dim)
         params = [(n, p) for n, p in model.named_parameters()]
@@ -106,7 +107,10 @@ class DataParallelTrainer:
                 missing = [n for n in self.names[:i] if n not in seen]
                 raise _lib.A3TError(f"backward produced no gradient for {missing[:4]}")
             if hi > lo and (final or hi - lo >= self.bucket_floats):
-                works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.xpg, async_op=True))
+                # ranges that run beside the sweep go to the (CTA-limited, high-priority) exchange communicator; the
+                # last one has nothing left to overlap with and takes the full-speed default communicator
+                grp = self.pg if (final and self.last_range_full_speed) else self.xpg
+                works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=grp, async_op=True))
                 self.exchange_ranges.append((lo, hi))
                 state["front"], state["hi"] = i, lo
 

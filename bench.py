@@ -472,6 +472,8 @@ def main():
     ap.add_argument("--diag-tiny-exchange", action="store_true",
                     help="diagnostic, N>1: no gradient exchange but a 16-byte all-reduce per step (cost of lock step alone)")
     ap.add_argument("--exchange-ctas", type=int, default=0, help="N>1: NCCL max_ctas of the gradient-exchange communicator (0 = NCCL default)")
+    ap.add_argument("--exchange-last-full", action="store_true",
+                    help="N>1 with --bucket-mb: the last gradient range (nothing left to overlap) uses the default communicator")
     ap.add_argument("--kernel-trace", default=None,
                     help="after the timed region: CUPTI kernel timeline (name, start, duration, stream, grid) of 2 steps on rank 0 -> CSV")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
@@ -508,7 +510,8 @@ def main():
         for n, p in model.named_parameters():
             if p.dim() == 1 and n.endswith("weight"):
                 p.fill_(1.0)
-    trainer = DataParallelTrainer(model, bucket_bytes=int(args.bucket_mb * (1 << 20)), exchange_max_ctas=args.exchange_ctas)
+    trainer = DataParallelTrainer(model, bucket_bytes=int(args.bucket_mb * (1 << 20)), exchange_max_ctas=args.exchange_ctas,
+                                  last_range_full_speed=args.exchange_last_full)
     if args.diag_no_exchange or args.diag_tiny_exchange:
         trainer.world = 1
     if args.diag_tiny_exchange:  # gradients stay local; one 16-byte all-reduce per step keeps the ranks in lock step
