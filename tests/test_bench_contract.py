@@ -27,3 +27,25 @@ def test_reference_arm_line():
     assert cb["cores"] > 1 or os.cpu_count() == 1, cb     # OMP_NUM_THREADS=1 from the launcher was not inherited
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"]
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """N > 1: the driver launches the reference arm with torchrun like the GPU arm; rank 0 alone measures and prints,
+    the other ranks exit 0 without work, and the launcher's OMP_NUM_THREADS=1 does not reach the measurement."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-batch", "1"],
+                       capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0
+    assert j["cpu_baseline"]["cores"] > 1 or os.cpu_count() == 1
